@@ -1,0 +1,457 @@
+// eig.cu -- eigen-decomposition of the small symmetric PSD Gram matrix G = W'W (n <= 512) by one-sided
+// (Hestenes) Jacobi with warp-shuffle rotations.  sigma_i = sqrt(lambda_i) and V are exactly what the reference
+// takes from LAPACK dgesdd (src/robustPCA.jl:194) -- the left factor is never needed because
+// A = U_r (S_r - 1/mu) V_r' = W V_r diag(1 - 1/(mu s_i)) V_r'.
+//
+// Invariant: X = G * V with V orthogonal.  Plane rotations are applied to column pairs of X (and V) until the
+// columns of X are mutually orthogonal; then X = V * Lambda.  Warm start: V0 = eigenvectors of the previous ALM
+// iteration, X0 = G * V0 is already nearly orthogonal, so 1-3 sweeps suffice instead of 6-10.
+//
+// Two engines:
+//  * jacobi_cluster_kernel (n <= 256): ONE thread-block cluster of up to 16 CTAs holds all columns (X and V parts,
+//    double buffered) in distributed shared memory.  One warp per column pair; the round-robin tournament moves
+//    every column one seat per round, written straight into the destination CTA's shared memory (DSMEM stores),
+//    one cluster barrier per round.  Dot products use warp-shuffle reductions; rotations happen in registers.
+//  * jacobi_global_kernel (any n <= 512): cooperative grid, columns stay in L2, grid barrier per round.
+#include <cooperative_groups.h>
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace tlsq {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// X0 = G * V  (n x n x n, plain FP64 FMA with 32x32 shared tiles; ~17 MFMA at n=256 -> microseconds)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_small_kernel(const double* __restrict__ G, const double* __restrict__ V, int n, double* __restrict__ X) {
+    __shared__ double Gs[32][33];
+    __shared__ double Vsm[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty in 0..7
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < n; k0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int kk = ty + 8 * r;
+            // Gs[kk][tx] = G[i0+tx, k0+kk]   (column-major, symmetric)
+            Gs[kk][tx] = (i0 + tx < n && k0 + kk < n) ? G[(int64_t)(k0 + kk) * n + i0 + tx] : 0.0;
+            // Vsm[kk][tx] = V[k0+tx, j0+kk]
+            Vsm[kk][tx] = (k0 + tx < n && j0 + kk < n) ? V[(int64_t)(j0 + kk) * n + k0 + tx] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int jj = ty + 8 * r;
+            double a = acc[r];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) a = fma(Gs[kk][tx], Vsm[jj][kk], a);
+            acc[r] = a;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int jj = ty + 8 * r;
+        if (i0 + tx < n && j0 + jj < n) X[(int64_t)(j0 + jj) * n + i0 + tx] = acc[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rotation of one column pair held in registers (E doubles per lane per column part)
+// returns true if a rotation was applied
+// ---------------------------------------------------------------------------------------------------
+template <int E>
+__device__ __forceinline__ bool jacobi_rotate(double (&xp)[E], double (&xq)[E], double (&vp)[E], double (&vq)[E],
+                                              double tol) {
+    double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        alpha = fma(xp[e], xp[e], alpha);
+        beta = fma(xq[e], xq[e], beta);
+        gamma = fma(xp[e], xq[e], gamma);
+    }
+    alpha = warp_sum(alpha);
+    beta = warp_sum(beta);
+    gamma = warp_sum(gamma);
+    const double lim = tol * sqrt(alpha) * sqrt(beta);
+    if (!(fabs(gamma) > lim) || lim == 0.0) return false;      // already orthogonal (or a null column)
+    const double zeta = (beta - alpha) / (2.0 * gamma);
+    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+    const double c = 1.0 / sqrt(fma(tt, tt, 1.0));
+    const double s = c * tt;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const double a = xp[e], b = xq[e];
+        xp[e] = fma(c, a, -s * b);
+        xq[e] = fma(s, a, c * b);
+        const double va = vp[e], vb = vq[e];
+        vp[e] = fma(c, va, -s * vb);
+        vq[e] = fma(s, va, c * vb);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cluster engine.  m = C * spc seats, seat s holds the pair (top[s], bot[s]); CTA c owns seats
+// [c*spc, (c+1)*spc).  Slot layout per buffer: slot (2*ls + which) * 2*LEN doubles = [X part | V part].
+// Tournament step (circle method): top[0] fixed; top[s] -> top[s+1] (1 <= s <= m-2); top[m-1] -> bot[m-1];
+// bot[s] -> bot[s-1] (s >= 1); bot[0] -> top[1].  (m == 1: nothing moves.)
+// ---------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256)
+jacobi_cluster_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n, int spc,
+                      double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
+                      int* __restrict__ info) {
+    constexpr int LEN = 32 * E;
+    extern __shared__ double smem[];
+    __shared__ int counters[64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int c = (int)cluster.block_rank();
+    const int m = C * spc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot_doubles = 2 * LEN;
+    const int buf_doubles = 2 * spc * slot_doubles;
+    double* buf0 = smem;
+    double* buf1 = smem + buf_doubles;
+
+    if (threadIdx.x < 64) counters[threadIdx.x] = 0;
+
+    // initial load: column j -> seat j/2, top if j even else bot.  Columns >= n are zero dummies.
+    for (int w = warp; w < 2 * spc; w += 8) {
+        const int ls = w >> 1, which = w & 1;
+        const int j = 2 * (c * spc + ls) + which;
+        double* dst = buf0 + (2 * ls + which) * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane + 32 * e;
+            double xv = 0.0, vv = 0.0;
+            if (j < n && i < n) {
+                xv = X0[(int64_t)j * n + i];
+                vv = V0 ? V0[(int64_t)j * n + i] : (i == j ? 1.0 : 0.0);
+            }
+            dst[i] = xv;
+            dst[LEN + i] = vv;
+        }
+    }
+    cluster.sync();
+
+    int* counters0 = cluster.map_shared_rank(counters, 0);
+    double* cur = buf0;
+    double* nxt = buf1;
+    int sweep = 0;
+    const int rounds = 2 * m - 1;
+    for (; sweep < max_sweeps; ++sweep) {
+        bool rotated = false;
+        for (int round = 0; round < rounds; ++round) {
+            if (warp < spc) {
+                const int ls = warp;
+                const int s = c * spc + ls;
+                double xp[E], xq[E], vp[E], vq[E];
+                const double* pt = cur + (2 * ls) * slot_doubles;
+                const double* pb = cur + (2 * ls + 1) * slot_doubles;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    xp[e] = pt[lane + 32 * e];
+                    vp[e] = pt[LEN + lane + 32 * e];
+                    xq[e] = pb[lane + 32 * e];
+                    vq[e] = pb[LEN + lane + 32 * e];
+                }
+                rotated |= jacobi_rotate<E>(xp, xq, vp, vq, tol);
+                // destinations
+                int ts, tw, bs, bw;            // seat / which for the top and bottom column
+                if (m == 1) { ts = 0; tw = 0; bs = 0; bw = 1; }
+                else {
+                    if (s == 0) { ts = 0; tw = 0; }
+                    else if (s == m - 1) { ts = m - 1; tw = 1; }
+                    else { ts = s + 1; tw = 0; }
+                    if (s == 0) { bs = 1; bw = 0; }
+                    else { bs = s - 1; bw = 1; }
+                }
+                {
+                    const int dc = ts / spc, dl = ts - dc * spc;
+                    double* base = (dc == c) ? nxt : cluster.map_shared_rank(nxt, dc);
+                    double* dst = base + (2 * dl + tw) * slot_doubles;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        dst[lane + 32 * e] = xp[e];
+                        dst[LEN + lane + 32 * e] = vp[e];
+                    }
+                }
+                {
+                    const int dc = bs / spc, dl = bs - dc * spc;
+                    double* base = (dc == c) ? nxt : cluster.map_shared_rank(nxt, dc);
+                    double* dst = base + (2 * dl + bw) * slot_doubles;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        dst[lane + 32 * e] = xq[e];
+                        dst[LEN + lane + 32 * e] = vq[e];
+                    }
+                }
+            }
+            cluster.sync();
+            double* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        if (rotated && lane == 0) atomicAdd(counters0 + sweep, 1);
+        cluster.sync();
+        const int cnt = *((volatile int*)(counters0 + sweep));
+        if (cnt == 0) { ++sweep; break; }
+    }
+    cluster.sync();   // nobody may exit while a peer still reads counters0 / writes DSMEM
+
+    // write back: column index = 2*seat + which (order is irrelevant; eig_post sorts)
+    for (int w = warp; w < 2 * spc; w += 8) {
+        const int ls = w >> 1, which = w & 1;
+        const int j = 2 * (c * spc + ls) + which;
+        const double* src = cur + (2 * ls + which) * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane + 32 * e;
+            if (i < n) {
+                Xo[(int64_t)j * n + i] = src[i];
+                Vo[(int64_t)j * n + i] = src[LEN + i];
+            }
+        }
+    }
+    if (c == 0 && threadIdx.x == 0) info[0] = sweep;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Global-memory engine (cooperative launch): columns live in Xo / Vo (L2 resident), one warp per pair.
+// ---------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256)
+jacobi_global_kernel(int n, int np, double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
+                     int* __restrict__ info) {
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int npairs = np / 2;
+    int* counters = info + 2;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        bool rotated = false;
+        for (int round = 0; round < np - 1; ++round) {
+            for (int pi = gw; pi < npairs; pi += nw) {
+                int p, q;
+                if (pi == 0) { p = np - 1; q = round; }
+                else { p = (round + pi) % (np - 1); q = (round - pi + (np - 1)) % (np - 1); }
+                if (p >= n || q >= n) continue;
+                double xp[E], xq[E], vp[E], vq[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = lane + 32 * e;
+                    const bool ok = i < n;
+                    xp[e] = ok ? __ldcg(Xo + (int64_t)p * n + i) : 0.0;
+                    xq[e] = ok ? __ldcg(Xo + (int64_t)q * n + i) : 0.0;
+                    vp[e] = ok ? __ldcg(Vo + (int64_t)p * n + i) : 0.0;
+                    vq[e] = ok ? __ldcg(Vo + (int64_t)q * n + i) : 0.0;
+                }
+                if (jacobi_rotate<E>(xp, xq, vp, vq, tol)) {
+                    rotated = true;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int i = lane + 32 * e;
+                        if (i < n) {
+                            __stcg(Xo + (int64_t)p * n + i, xp[e]);
+                            __stcg(Xo + (int64_t)q * n + i, xq[e]);
+                            __stcg(Vo + (int64_t)p * n + i, vp[e]);
+                            __stcg(Vo + (int64_t)q * n + i, vq[e]);
+                        }
+                    }
+                }
+            }
+            grid.sync();
+        }
+        if (rotated && lane == 0) atomicAdd(counters + sweep, 1);
+        grid.sync();
+        const int cnt = *((volatile int*)(counters + sweep));
+        if (cnt == 0) { ++sweep; break; }
+    }
+    if (gw == 0 && lane == 0) info[0] = sweep;
+}
+
+// prepare Xo/Vo for the global engine: Xo = X0 (or G), Vo = V0 (or I)
+__global__ void jacobi_global_init_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n,
+                                          double* __restrict__ Xo, double* __restrict__ Vo, int* __restrict__ info) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 66) info[idx] = 0;
+    if (idx >= (int64_t)n * n) return;
+    const int i = (int)(idx % n), j = (int)(idx / n);
+    Xo[idx] = X0[idx];
+    Vo[idx] = V0 ? V0[idx] : (i == j ? 1.0 : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// post-processing: lambda_j = v_j . x_j, rank (descending), perm; dummy columns (v == 0) are dropped
+// single CTA, 256 threads
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eig_post_kernel(const double* __restrict__ Xo, const double* __restrict__ Vo, int n, int ncols,
+                double* __restrict__ lam_raw, double* __restrict__ lam_sorted, int* __restrict__ perm) {
+    extern __shared__ double sl[];          // ncols lam + ncols valid flags (as double)
+    double* lam = sl;
+    double* valid = sl + ncols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < ncols; j += 8) {
+        double dot = 0.0, vv = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double v = Vo[(int64_t)j * n + i];
+            dot = fma(v, Xo[(int64_t)j * n + i], dot);
+            vv = fma(v, v, vv);
+        }
+        dot = warp_sum(dot);
+        vv = warp_sum(vv);
+        if (lane == 0) {
+            lam[j] = dot;
+            valid[j] = (vv > 0.5) ? 1.0 : 0.0;
+            lam_raw[j] = dot;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncols; j += blockDim.x) {
+        if (valid[j] == 0.0) continue;
+        const double lj = lam[j];
+        int rank = 0;
+        for (int k = 0; k < ncols; ++k) {
+            if (valid[k] == 0.0) continue;
+            const double lk = lam[k];
+            rank += (lk > lj) || (lk == lj && k < j);
+        }
+        if (rank < n) {
+            perm[rank] = j;
+            lam_sorted[rank] = lj;
+        }
+    }
+}
+
+// Vs[:, r] = Vo[:, perm[r]]
+__global__ void permute_cols_kernel(const double* __restrict__ Vo, const int* __restrict__ perm, int n,
+                                    double* __restrict__ Vs) {
+    const int r = blockIdx.x;
+    const int j = perm[r];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) Vs[(int64_t)r * n + i] = Vo[(int64_t)j * n + i];
+}
+
+__global__ void svt_post_kernel(const double* __restrict__ lam, int n, double tau, int nukeA,
+                                double* __restrict__ sigma, double* __restrict__ fvec, int* __restrict__ svp) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double l = lam[i];
+        const double sg = l > 0.0 ? sqrt(l) : 0.0;
+        sigma[i] = sg;
+        const bool keep = sg >= tau;                                   // s.S .>= 1/mu   (src/robustPCA.jl:198)
+        local += keep ? 1 : 0;
+        // A = U_r diag(S_r - 1/mu) V_r' = W V_r diag((S_r - 1/mu)/S_r) V_r'   (:207-208);  nukeA=false: factor 1
+        fvec[i] = keep ? (nukeA ? (sg - tau) / sg : 1.0) : 0.0;
+    }
+    if (local) atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) *svp = cnt;
+}
+
+template <int E>
+cudaError_t launch_cluster(const double* X0, const double* V0, int n, int C, int spc, double tol, int max_sweeps,
+                           double* Xo, double* Vo, int* info, cudaStream_t st) {
+    constexpr int LEN = 32 * E;
+    const size_t smem = (size_t)2 * 2 * spc * 2 * LEN * sizeof(double);
+    auto kern = jacobi_cluster_kernel<E>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (C > 8) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, X0, V0, n, spc, tol, max_sweeps, Xo, Vo, info);
+}
+
+template <int E>
+cudaError_t launch_global(int n, int np, double tol, int max_sweeps, double* Xo, double* Vo, int* info,
+                          int sm_count, cudaStream_t st) {
+    int npairs = np / 2;
+    int blocks = (npairs + 7) / 8;
+    if (blocks > sm_count) blocks = sm_count;
+    if (blocks < 1) blocks = 1;
+    void* args[] = {&n, &np, &tol, &max_sweeps, &Xo, &Vo, &info};
+    return cudaLaunchCooperativeKernel((void*)jacobi_global_kernel<E>, dim3(blocks), dim3(256), args, 0, st);
+}
+
+}  // namespace
+
+size_t eig_work_doubles(int n) {
+    const size_t np = (size_t)n + 34;          // padded column count upper bound
+    // X0 (n*n) + Xo (np*n) + Vo (np*n) + lam_raw (np) + perm (n ints -> n doubles) + info (66 ints -> 64 doubles)
+    return (size_t)n * n + 2 * np * n + np + n + 64 + 16;
+}
+
+cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
+                        int sm_count, cudaStream_t st, int64_t* launches) {
+    cudaError_t e;
+    const double tol = 1.0e-15 * (n < 16 ? 4.0 : sqrt((double)n));   // relative orthogonality threshold
+    const int max_sweeps = 30;
+    const double* X0 = G;
+    if (V0) {
+        dim3 grid((n + 31) / 32, (n + 31) / 32);
+        gemm_small_kernel<<<grid, 256, 0, st>>>(G, V0, n, w.X0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 1;
+        X0 = w.X0;
+    }
+    int ncols;
+    if (n <= 256) {
+        // seats m >= ceil(n/2); cluster size C in {1,2,4,8,16}, seats per CTA spc <= 8
+        const int mneed = (n + 1) / 2;
+        int C = 1;
+        while (C < 16 && (mneed + C - 1) / C > 8) C *= 2;
+        const int spc = (mneed + C - 1) / C;
+        ncols = 2 * C * spc;
+        if (n <= 32) e = launch_cluster<1>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
+        else if (n <= 64) e = launch_cluster<2>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
+        else if (n <= 128) e = launch_cluster<4>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
+        else e = launch_cluster<8>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
+        if (e != cudaSuccess) return e;
+        if (launches) *launches += 1;
+    } else {
+        const int np = (n + 1) & ~1;
+        ncols = n;
+        jacobi_global_init_kernel<<<(unsigned)(((int64_t)n * n + 255) / 256), 256, 0, st>>>(X0, V0, n, w.Xo, w.Vo,
+                                                                                           w.info);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        e = launch_global<16>(n, np, tol, max_sweeps, w.Xo, w.Vo, w.info, sm_count, st);
+        if (e != cudaSuccess) return e;
+        if (launches) *launches += 2;
+    }
+    eig_post_kernel<<<1, 256, 2 * ncols * sizeof(double), st>>>(w.Xo, w.Vo, n, ncols, w.lam_raw, lam, w.perm);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    permute_cols_kernel<<<n, 128, 0, st>>>(w.Vo, w.perm, n, Vs);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_svt_post(const double* lam, int n, double tau, int nukeA, double* sigma, double* fvec,
+                            int* svp, cudaStream_t st, int64_t* launches) {
+    svt_post_kernel<<<1, 256, 0, st>>>(lam, n, tau, nukeA, sigma, fvec, svp);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace tlsq

@@ -1,0 +1,164 @@
+// elementwise.cu -- streaming helper kernels: max|D| (src/robustPCA.jl:178), Y = D/dual & A = 0 (:174-181),
+// E recomputation for the returned value (:188-191,238), transpose (M < N inputs), hankel / unhankel
+// (:76-92, :28-39, :53-68).
+#include "kernels.h"
+
+namespace tlsq {
+
+namespace {
+
+template <bool HANKEL>
+__global__ void __launch_bounds__(256)
+maxabs_kernel(const MatSrc D, int64_t M, int64_t N, double* __restrict__ out) {
+    const int64_t total = M * N;
+    double m = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx % M, col = idx / M;
+        m = fmax(m, fabs(src_at<HANKEL>(D, row, col)));
+    }
+    m = warp_max(m);
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+template <bool HANKEL>
+__global__ void __launch_bounds__(256)
+init_ya_kernel(const MatSrc D, int64_t M, int64_t N, double dual, double* __restrict__ Y, double* __restrict__ A) {
+    const int64_t total = M * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx % M, col = idx / M;
+        Y[idx] = __ddiv_rn(src_at<HANKEL>(D, row, col), dual);      // Y ./= dual_norm   (:181)
+        A[idx] = 0.0;
+    }
+}
+
+template <bool HANKEL>
+__global__ void __launch_bounds__(256)
+compute_e_kernel(const MatSrc D, int64_t M, int64_t N, const double* __restrict__ A, const double* __restrict__ Y,
+                 double im, double eps, int nonnegE, double* __restrict__ E) {
+    const int64_t total = M * N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx % M, col = idx / M;
+        double e, w;
+        alm_ew(src_at<HANKEL>(D, row, col), A[idx], Y[idx], im, eps, nonnegE, e, w);
+        E[idx] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ in, int64_t M, int64_t N, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t i = i0 + tx, j = j0 + ty + 8 * r;
+        if (i < M && j < N) tile[ty + 8 * r][tx] = in[j * M + i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t j = j0 + tx, i = i0 + ty + 8 * r;
+        if (i < M && j < N) out[i * N + j] = tile[tx][ty + 8 * r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hankel_kernel(const double* __restrict__ x, int64_t K, int64_t L, int64_t lag, double* __restrict__ H) {
+    const int64_t total = K * L;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = idx % K, l = idx / K;
+        H[idx] = x[k * lag + l];                                     // X[k, l] = x[(k-1)lag + l]   (:87-88)
+    }
+}
+
+// y[t] = mean over {(k,l): k*lag + l == t} of A[k,l]; entries are visited for increasing l (column-major order of
+// the reference's accumulation, :62-65); for lag == 1 this is the anti-diagonal mean (:28-39).
+__global__ void __launch_bounds__(256)
+unhankel_kernel(const double* __restrict__ A, int64_t K, int64_t L, int64_t lag, int64_t Ns,
+                double* __restrict__ y) {
+    for (int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tt < Ns;
+         tt += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        int64_t cnt = 0;
+        for (int64_t l = 0; l < L; ++l) {
+            const int64_t rem = tt - l;
+            if (rem < 0) break;
+            if (rem % lag) continue;
+            const int64_t k = rem / lag;
+            if (k >= K) continue;
+            s += A[l * K + k];
+            ++cnt;
+        }
+        y[tt] = s / (double)(cnt > 0 ? cnt : 1);                     // y ./= max.(counts, 1)   (:66)
+    }
+}
+
+inline int stream_grid(int64_t total, int sm_count) {
+    int64_t want = (total + 255) / 256;
+    int64_t cap = (int64_t)sm_count * 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+}  // namespace
+
+cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, double* out, int sm_count,
+                          cudaStream_t st, int64_t* launches) {
+    const int grid = stream_grid(M * N, sm_count);
+    if (hankel) maxabs_kernel<true><<<grid, 256, 0, st>>>(D, M, N, out);
+    else maxabs_kernel<false><<<grid, 256, 0, st>>>(D, M, N, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A,
+                           int sm_count, cudaStream_t st, int64_t* launches) {
+    const int grid = stream_grid(M * N, sm_count);
+    if (hankel) init_ya_kernel<true><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A);
+    else init_ya_kernel<false><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N, const double* A, const double* Y,
+                             double im, double eps, int nonnegE, double* E, int sm_count, cudaStream_t st,
+                             int64_t* launches) {
+    const int grid = stream_grid(M * N, sm_count);
+    if (hankel) compute_e_kernel<true><<<grid, 256, 0, st>>>(D, M, N, A, Y, im, eps, nonnegE, E);
+    else compute_e_kernel<false><<<grid, 256, 0, st>>>(D, M, N, A, Y, im, eps, nonnegE, E);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const double* in, int64_t M, int64_t N, double* out, cudaStream_t st,
+                             int64_t* launches) {
+    dim3 grid((unsigned)((M + 31) / 32), (unsigned)((N + 31) / 32));
+    transpose_kernel<<<grid, 256, 0, st>>>(in, M, N, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hankel(const double* x, int64_t K, int64_t L, int64_t lag, double* H, cudaStream_t st,
+                          int64_t* launches) {
+    const int grid = stream_grid(K * L, 148);
+    hankel_kernel<<<grid, 256, 0, st>>>(x, K, L, lag, H);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unhankel(const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, double* y,
+                            cudaStream_t st, int64_t* launches) {
+    const int grid = stream_grid(Ns, 148);
+    unhankel_kernel<<<grid, 256, 0, st>>>(A, K, L, lag, Ns, y);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace tlsq

@@ -1,0 +1,130 @@
+// kernels.h -- internal launcher interface between the host solver (solver.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace tlsq {
+
+// ----------------------------------------------------------------------------------------------------
+// Gram (SYRK) pass: G = W'W where W is formed on the fly per element.
+// ----------------------------------------------------------------------------------------------------
+enum GramMode : int {
+    GRAM_D = 0,   // W = D                                  (opnorm(D), src/robustPCA.jl:177)
+    GRAM_W = 1,   // W = D - E + Y/mu, E = soft_th(...)     (SVT input, :188-194)
+    GRAM_Z = 2    // W = Z = D - A_new - E                  (exact stop test opnorm(Z), :221,225)
+};
+
+struct GramSrc {
+    MatSrc D;            // dense matrix or implicit Hankel signal
+    const double* A;     // A_{k-1}  (modes W, Z)   ld = ldw
+    const double* Y;     // Y_{k-1}  (modes W, Z)
+    const double* A2;    // A_k      (mode Z)
+    int64_t ldw;         // leading dimension of A / Y / A2
+    int64_t M, N;
+    double im, eps;      // 1/mu, lambda/mu
+    int nonnegE;
+};
+
+constexpr int kGramBlk = 64;   // output block edge handled by one CTA
+constexpr int kGramRows = 32;  // rows (K dimension) per smem tile
+
+// number of upper-triangular blocks / CTA split over rows chosen by the launcher
+struct GramPlan { int nb; int nblk; int nsplit; int ntiles; size_t partial_bytes; };
+GramPlan gram_plan(int64_t M, int64_t N, int sm_count);
+// partial: workspace of plan.partial_bytes; G: N x N (ld N), full symmetric
+cudaError_t launch_gram(const GramSrc& s, GramMode mode, bool hankel, const GramPlan& plan, double* partial,
+                        double* G, cudaStream_t st, int64_t* launches);
+
+// ----------------------------------------------------------------------------------------------------
+// Small symmetric eigenproblem (n <= 512): one-sided Jacobi with warp-shuffle rotations.
+// ----------------------------------------------------------------------------------------------------
+struct EigWork {       // all device pointers, sized for n (see eig_work_bytes)
+    double* X0;        // n x n    G * V0
+    double* Xo;        // npad x n rotated columns (X part)
+    double* Vo;        // npad x n rotated columns (V part)
+    double* lam_raw;   // npad
+    int*    perm;      // n
+    int*    info;      // [0] sweeps done, [1] rotations in last sweep, [2..] per-sweep counters (64)
+};
+size_t eig_work_doubles(int n);
+constexpr int kEigMaxN = 512;
+// Eigen-decomposition of symmetric PSD G (n x n, ld n).  If V0 != nullptr it must hold an orthogonal n x n
+// warm-start basis (previous eigenvectors).  Outputs: lam (n, descending), Vs (n x n sorted eigenvector columns).
+// Vs may alias V0.
+cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
+                        int sm_count, cudaStream_t st, int64_t* launches);
+
+// sigma[i] = sqrt(max(lam[i],0)); svp = #{sigma >= tau}; fvec[i] = nuke ? (sigma-tau)/sigma : 1  (0 beyond svp)
+cudaError_t launch_svt_post(const double* lam, int n, double tau, int nukeA, double* sigma, double* fvec,
+                            int* svp, cudaStream_t st, int64_t* launches);
+
+// ----------------------------------------------------------------------------------------------------
+// Fused ALM epilogue: one pass over a row tile does  E-step, W, T = W V_r, A = clamp(T diag(f) V_r'),
+// Z = D - A - E, Y += mu Z, ||Z||_F^2   (src/robustPCA.jl:188-192, 205-222)
+// ----------------------------------------------------------------------------------------------------
+struct EpiArgs {
+    MatSrc D;
+    const double* Ap;   // A_{k-1}
+    const double* Yp;   // Y_{k-1}
+    double* An;         // A_k      (may alias Ap: the pass is tile-local)
+    double* Yn;         // Y_k      (may alias Yp)
+    double* Eout;       // optional E_k
+    double* Uout;       // MODE U only: M x d
+    int64_t M, N, ldw;
+    const double* Vs;   // N x N sorted right singular vectors (ld N)
+    const double* fvec; // N shrink factors (MODE U: 1/sigma)
+    const int* svp;     // device scalar: number of columns of Vs to use
+    double im, eps, mu;
+    int nonnegA, nonnegE;
+    double* zz;         // device scalar accumulator for ||Z||_F^2
+};
+cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_count, cudaStream_t st,
+                            int64_t* launches);
+
+// element-wise helpers ------------------------------------------------------------------------------
+// maxabs: *out = max |D_ij| (out must be zeroed);  init: Y = D / dual, A = 0
+cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, double* out, int sm_count,
+                          cudaStream_t st, int64_t* launches);
+cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A,
+                           int sm_count, cudaStream_t st, int64_t* launches);
+// E = soft_th((D - A) + Y/mu, lambda/mu) (+ clamp)
+cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N, const double* A, const double* Y,
+                             double im, double eps, int nonnegE, double* E, int sm_count, cudaStream_t st,
+                             int64_t* launches);
+// out (N x M) = in (M x N)'
+cudaError_t launch_transpose(const double* in, int64_t M, int64_t N, double* out, cudaStream_t st,
+                             int64_t* launches);
+
+// hankel / unhankel (single channel) ------------------------------------------------------------------
+cudaError_t launch_hankel(const double* x, int64_t K, int64_t L, int64_t lag, double* H, cudaStream_t st,
+                          int64_t* launches);
+cudaError_t launch_unhankel(const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, double* y,
+                            cudaStream_t st, int64_t* launches);
+
+// Grassmann averages ----------------------------------------------------------------------------------
+enum GaMode : int {
+    GA_NORMS = 0,   // t[n] += sum_i X[i,n]^2                                   (src/robustPCA.jl:265)
+    GA_DOTS  = 1,   // t[n] += sum_i X[i,n] q[i]                                (:271, and the first :291-293)
+    GA_PASS  = 2    // mu_i = (sum_n s[n] X[i,n]) / sumw ; t[n] += sum_i X[i,n] mu_i ; t[N] += sum_i mu_i^2
+};                  //                                                          (:291-294, 308-316 in ONE sweep)
+// X: d x N (ld), vec: q (GA_DOTS, length d) or mu out (GA_PASS, length d); s: N sign weights; sumw: device scalar
+cudaError_t launch_ga_sweep(GaMode mode, const double* X, int64_t d, int64_t N, int64_t ld, double* vec,
+                            const double* s, const double* sumw, double* t, int sm_count, cudaStream_t st,
+                            int64_t* launches);
+// s[n] = sign(t[n]) (0 if norms[n]==0), sumw = sum_n s[n]*norms[n]            (:292, :310-312)
+cudaError_t launch_ga_signs(const double* t, const double* norms2, int64_t N, double* s, double* sumw,
+                            cudaStream_t st, int64_t* launches);
+// q = mu / sqrt(mm);  dq2 += sum (q - qold)^2;  qold <- q   (:295-296, 302)   (mm, dq2 device scalars)
+cudaError_t launch_ga_update(const double* mu, const double* mm, int64_t d, double* q, double* dq2, int sm_count,
+                             cudaStream_t st, int64_t* launches);
+// ss += sum_i v[i]^2 ;  scale: v *= 1/sqrt(ss)
+cudaError_t launch_vec_sumsq(const double* v, int64_t d, double* ss, int sm_count, cudaStream_t st,
+                             int64_t* launches);
+cudaError_t launch_vec_scale_rsqrt(const double* v, const double* ss, int64_t d, double* out, int sm_count,
+                                   cudaStream_t st, int64_t* launches);
+// X[i,n] -= q[i] * xs[n]    (:272)
+cudaError_t launch_ga_deflate(double* X, int64_t d, int64_t N, int64_t ld, const double* q, const double* xs,
+                              int sm_count, cudaStream_t st, int64_t* launches);
+
+}  // namespace tlsq

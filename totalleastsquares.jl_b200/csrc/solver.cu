@@ -1,0 +1,737 @@
+// solver.cu -- host orchestration behind the C ABI (include/tlsq_b200.h): handle, NCCL plumbing (dlopen, so the
+// library loads on machines without NCCL or a GPU), and the three solver loops
+//   rpca_core        inexact ALM               (src/robustPCA.jl:156-239)
+//   rpca_ga_core     Grassmann averages        (src/robustPCA.jl:255-306)
+//   lowrankfilter    rpca on an implicit Hankel embedding + anti-diagonal averaging (:119-128)
+// There is no CPU fallback anywhere in this file: every path launches the sm_100a kernels or fails.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/tlsq_b200.h"
+#include "kernels.h"
+
+using namespace tlsq;
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            int _code = (_e == cudaErrorMemoryAllocation) ? TLSQ_ERR_NOMEM : TLSQ_ERR_CUDA;              \
+            return set_err(_code, "CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(_e), __FILE__,     \
+                           __LINE__, #expr);                                                             \
+        }                                                                                                \
+    } while (0)
+
+#define CKR(expr)                                \
+    do {                                         \
+        int _r = (expr);                         \
+        if (_r != TLSQ_OK) return _r;            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+typedef int (*fn_get_uid)(NcclId*);
+typedef int (*fn_init_rank)(void**, int, NcclId, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+typedef const char* (*fn_errstr)(int);
+
+struct NcclApi {
+    void* lib = nullptr;
+    fn_get_uid get_uid = nullptr;
+    fn_init_rank init_rank = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_errstr errstr = nullptr;
+    bool tried = false;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+
+int nccl_load() {
+    if (g_nccl.lib) return TLSQ_OK;
+    if (!g_nccl.tried) {
+        g_nccl.tried = true;
+        const char* env = getenv("TLSQ_NCCL_LIB");
+        const char* cands[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* c : cands) {
+            if (!c || !*c) continue;
+            g_nccl.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+        if (g_nccl.lib) {
+            g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.lib, "ncclGetUniqueId");
+            g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.lib, "ncclCommInitRank");
+            g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+            g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+            g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+            if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy) g_nccl.lib = nullptr;
+        }
+    }
+    if (!g_nccl.lib)
+        return set_err(TLSQ_ERR_NCCL, "libnccl.so.2 not loadable (set TLSQ_NCCL_LIB to its path): %s",
+                       dlerror() ? dlerror() : "symbols missing");
+    return TLSQ_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------------
+struct tlsq_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    void* comm = nullptr;
+    int nranks = 1;
+    int rank = 0;
+    double* h_pin = nullptr;     // pinned host scratch (64 doubles)
+};
+
+namespace {
+
+struct DevBuf {                  // stream-ordered device allocation, freed on scope exit
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        if (bytes == 0) bytes = 8;
+        return cudaMallocAsync(&p, bytes, s);
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+int allreduce(tlsq_handle* h, double* buf, size_t count, int op) {
+    if (h->nranks <= 1) return TLSQ_OK;
+    int r = g_nccl.allreduce(buf, buf, count, kNcclFloat64, op, h->comm, h->stream);
+    if (r != 0) return set_err(TLSQ_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(r) : "?");
+    return TLSQ_OK;
+}
+
+int use_device(tlsq_handle* h) {
+    if (!h) return set_err(TLSQ_ERR_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    return TLSQ_OK;
+}
+
+struct RpcaParams {
+    double lambda, tol, rho;
+    int64_t maxrank, iters;
+    uint32_t flags;
+};
+struct RpcaOut {
+    double* A = nullptr;  double* E = nullptr;  double* U = nullptr;  double* S = nullptr;  double* Vt = nullptr;
+    int64_t* sv = nullptr;  int64_t* iters_done = nullptr;  int32_t* converged = nullptr;  double* hist = nullptr;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// rpca core: M (local rows) x N, M_global >= N, N <= kEigMaxN.  D may be dense or an implicit Hankel signal.
+// All outputs are DEVICE pointers (nullable) except sv / iters_done / converged / hist (host).
+// ----------------------------------------------------------------------------------------------------------
+int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const RpcaParams& p, const RpcaOut& o) {
+    cudaStream_t st = h->stream;
+    const int sms = h->sm_count;
+    int64_t* L = &h->launches;
+    const int n = (int)N;
+    const size_t mn = (size_t)M * (size_t)N;
+    const int nonnegA = (p.flags & TLSQ_NONNEG_A) ? 1 : 0;
+    const int nonnegE = (p.flags & TLSQ_NONNEG_E) ? 1 : 0;
+    const int nukeA = (p.flags & TLSQ_NO_NUKE_A) ? 0 : 1;
+    const bool exact_cost = (p.flags & TLSQ_EXACT_COST) != 0;
+
+    // global row count (for the Frobenius bracket: d = min(M_global, N))
+    double Mg = (double)M;
+    GramPlan plan = gram_plan(M, N, sms);
+
+    DevBuf bA0, bA1, bY0, bY1, bPart, bG, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
+    // A ping-pong: reuse the caller's A buffer as one side when given
+    double* Abuf[2];
+    if (o.A) Abuf[0] = o.A; else { CK(bA0.alloc(mn * 8, st)); Abuf[0] = bA0.as<double>(); }
+    CK(bA1.alloc(mn * 8, st)); Abuf[1] = bA1.as<double>();
+    CK(bY0.alloc(mn * 8, st)); CK(bY1.alloc(mn * 8, st));
+    double* Ybuf[2] = {bY0.as<double>(), bY1.as<double>()};
+    CK(bPart.alloc(plan.partial_bytes, st));
+    CK(bG.alloc((size_t)n * n * 8, st)); CK(bG2.alloc((size_t)n * n * 8, st));
+    CK(bVs.alloc((size_t)n * n * 8, st)); CK(bVs2.alloc((size_t)n * n * 8, st));
+    CK(bLam.alloc((size_t)n * 8, st)); CK(bLam2.alloc((size_t)n * 8, st));
+    CK(bSig.alloc((size_t)n * 8, st)); CK(bF.alloc((size_t)n * 8, st));
+    CK(bEig.alloc(eig_work_doubles(n) * 8, st));
+    CK(bScal.alloc(16 * 8, st)); CK(bSvp.alloc(16, st));
+    double* G = bG.as<double>(); double* G2 = bG2.as<double>();
+    double* Vs = bVs.as<double>(); double* Vs2 = bVs2.as<double>();
+    double* lam = bLam.as<double>(); double* lam2 = bLam2.as<double>();
+    double* sigma = bSig.as<double>(); double* fvec = bF.as<double>();
+    double* dscal = bScal.as<double>(); int* dsvp = bSvp.as<int>();
+    EigWork ew;
+    {
+        double* base = bEig.as<double>();
+        const size_t np = (size_t)n + 34;
+        ew.X0 = base; base += (size_t)n * n;
+        ew.Xo = base; base += np * n;
+        ew.Vo = base; base += np * n;
+        ew.lam_raw = base; base += np;
+        ew.perm = reinterpret_cast<int*>(base); base += n;
+        ew.info = reinterpret_cast<int*>(base);
+    }
+    double* hp = h->h_pin;
+
+    // ---- setup (:174-185) --------------------------------------------------------------------------------
+    CK(cudaMemsetAsync(dscal, 0, 16 * 8, st));
+    if (h->nranks > 1) {
+        hp[0] = Mg;
+        CK(cudaMemcpyAsync(dscal + 2, hp, 8, cudaMemcpyHostToDevice, st));
+        CKR(allreduce(h, dscal + 2, 1, kNcclSum));
+        CK(cudaMemcpyAsync(hp, dscal + 2, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        Mg = hp[0];
+    }
+    if (Mg < (double)N) return set_err(TLSQ_ERR_UNSUPPORTED, "internal: rpca_core needs M >= N");
+    const double dmin = (double)N;
+
+    GramSrc gs;
+    gs.D = D; gs.A = nullptr; gs.Y = nullptr; gs.A2 = nullptr; gs.ldw = M; gs.M = M; gs.N = N;
+    gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = nonnegE;
+    CK(launch_gram(gs, GRAM_D, hankel, plan, bPart.as<double>(), G, st, L));            // D'D
+    CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+    CK(launch_maxabs(D, hankel, M, N, dscal + 1, sms, st, L));                           // norm(Y, Inf)   :178
+    CKR(allreduce(h, dscal + 1, 1, kNcclMax));
+    CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));                             // opnorm(Y)      :177
+    CK(cudaMemcpyAsync(hp, lam, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 1, dscal + 1, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double norm2 = sqrt(hp[0] > 0.0 ? hp[0] : 0.0);
+    const double norminf = hp[1] / p.lambda;
+    const double dual_norm = norm2 > norminf ? norm2 : norminf;                          // :179
+    const double d_norm = norm2;                                                         // :180
+    double mu = 1.25 / norm2;                                                            // :182
+    const double mubar = mu * 1.0e7;                                                     // :183
+    CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], Abuf[0], sms, st, L));        // Y ./= dual_norm :181
+
+    int cur = 0;
+    int64_t k_done = 0;
+    int conv = 0;
+    int svp_last = 10;
+    double im_last = 0.0, eps_last = 0.0;
+    int prev_idx = 0, last_idx = 0;
+
+    for (int64_t k = 1; k <= p.iters; ++k) {                                             // :186
+        const int nxt = cur ^ 1;
+        const double im = 1.0 / mu;
+        const double eps = p.lambda / mu;
+        // SVT input Gram  (:188-194)
+        gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = nullptr; gs.im = im; gs.eps = eps;
+        CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+        CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+        CK(launch_eigh(G, n, Vs, ew, lam, Vs, sms, st, L));                              // warm start from V_{k-1}
+        CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L));                // :198
+        // fused epilogue  (:188-192, 205-222)
+        CK(cudaMemsetAsync(dscal, 0, 8, st));
+        EpiArgs ea;
+        ea.D = D; ea.Ap = Abuf[cur]; ea.Yp = Ybuf[cur]; ea.An = Abuf[nxt]; ea.Yn = Ybuf[nxt];
+        ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
+        ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
+        ea.zz = dscal;
+        CK(launch_epilogue(ea, hankel, false, sms, st, L));
+        CKR(allreduce(h, dscal, 1, kNcclSum));
+        CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const double zz = hp[0];
+        int svp;
+        memcpy(&svp, hp + 1, 4);
+        svp_last = svp;
+        im_last = im; eps_last = eps; prev_idx = cur; last_idx = nxt;
+        mu = fmin(mu * p.rho, mubar);                                                    // :223
+        // stop test  cost = opnorm(Z)/d_norm < tol   (:225-231)
+        const double fro = sqrt(zz) / d_norm;        // ||Z||_F/d_norm >= cost >= ||Z||_F/(sqrt(d) d_norm)
+        double cost_rec = -fro;
+        bool converged;
+        bool need_exact = exact_cost;
+        if (!need_exact) {
+            if (fro < p.tol) converged = true;
+            else if (fro / sqrt(dmin) >= p.tol) converged = false;
+            else need_exact = true;
+        }
+        if (need_exact) {
+            gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;
+            CK(launch_gram(gs, GRAM_Z, hankel, plan, bPart.as<double>(), G2, st, L));
+            CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
+            CK(launch_eigh(G2, n, nullptr, ew, lam2, Vs2, sms, st, L));
+            CK(cudaMemcpyAsync(hp, lam2, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const double cost = sqrt(hp[0] > 0.0 ? hp[0] : 0.0) / d_norm;
+            cost_rec = cost;
+            converged = cost < p.tol;
+        }
+        if (o.hist) {
+            o.hist[3 * (k - 1) + 0] = (double)k;
+            o.hist[3 * (k - 1) + 1] = (double)svp;
+            o.hist[3 * (k - 1) + 2] = cost_rec;
+        }
+        k_done = k;
+        cur = nxt;
+        if (converged) { conv = 1; break; }
+    }
+
+    // ---- outputs (:238) ----------------------------------------------------------------------------------
+    // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
+    // produced before A_k is copied there.
+    if (o.E)
+        CK(launch_compute_e(D, hankel, M, N, Abuf[prev_idx], Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
+                            st, L));
+    if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
+    if (o.U) {
+        // U[:, c] = W v_c / s_c  with W the last SVT input (recomputed from A_{k-1}, Y_{k-1})
+        std::vector<double> hs(n);
+        CK(cudaMemcpyAsync(hs.data(), sigma, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
+        CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
+        EpiArgs ea;
+        ea.D = D; ea.Ap = Abuf[prev_idx]; ea.Yp = Ybuf[prev_idx]; ea.An = nullptr; ea.Yn = nullptr;
+        ea.Eout = nullptr; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
+        ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last; ea.mu = 0.0; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
+        ea.zz = dscal;
+        CK(launch_epilogue(ea, hankel, true, sms, st, L));
+    }
+    if (o.A && Abuf[last_idx] != o.A)
+        CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if (o.sv) {
+        int64_t sv = svp_last;                                                           // :199-204
+        if (sv < 1) sv = 1;
+        if (p.maxrank > 0 && sv > p.maxrank) sv = p.maxrank;
+        *o.sv = sv;
+    }
+    if (o.iters_done) *o.iters_done = k_done;
+    if (o.converged) *o.converged = conv;
+    return TLSQ_OK;
+}
+
+int check_rpca_args(int64_t M, int64_t N, const RpcaParams& p) {
+    if (M < 1 || N < 1) return set_err(TLSQ_ERR_ARG, "rpca: empty matrix (%lld x %lld)", (long long)M, (long long)N);
+    if (p.iters < 1) return set_err(TLSQ_ERR_ARG, "rpca: iters must be >= 1");
+    if (!(p.lambda > 0.0)) return set_err(TLSQ_ERR_ARG, "rpca: lambda must be > 0");
+    if (!(p.rho > 0.0)) return set_err(TLSQ_ERR_ARG, "rpca: rho must be > 0");
+    if (p.flags & TLSQ_HANKEL)
+        return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: hankel=true (soft_hankel!) is outside the accelerated path");
+    return TLSQ_OK;
+}
+
+// dense rpca on device pointers, any orientation (M < N is solved on the transpose: the problem is
+// transpose-invariant -- nuclear / l1 / spectral norms and lambda = 1/sqrt(max(M,N)) all are)
+int rpca_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, const RpcaParams& p, const RpcaOut& o) {
+    CKR(check_rpca_args(M, N, p));
+    cudaStream_t st = h->stream;
+    const bool tall = (M >= N) || h->nranks > 1;
+    const int64_t nn = tall ? N : M;
+    if (nn > kEigMaxN)
+        return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: min(M,N) = %lld exceeds the supported %d", (long long)nn,
+                       kEigMaxN);
+    if (tall) {
+        MatSrc src{D, M};
+        return rpca_core(h, src, false, M, N, p, o);
+    }
+    // wide: solve on D' (N x M)
+    const size_t mn = (size_t)M * N;
+    DevBuf bDt, bAt, bEt, bUt, bVtt;
+    CK(bDt.alloc(mn * 8, st));
+    CK(launch_transpose(D, M, N, bDt.as<double>(), st, &h->launches));
+    RpcaOut ot = o;
+    ot.A = nullptr; ot.E = nullptr; ot.U = nullptr; ot.Vt = nullptr;
+    if (o.A) { CK(bAt.alloc(mn * 8, st)); ot.A = bAt.as<double>(); }
+    if (o.E) { CK(bEt.alloc(mn * 8, st)); ot.E = bEt.as<double>(); }
+    const int64_t d = M;                       // min(M, N)
+    if (o.Vt) { CK(bUt.alloc((size_t)N * d * 8, st)); ot.U = bUt.as<double>(); }    // U' of D' is N x d  -> Vt = U''
+    if (o.U) { CK(bVtt.alloc((size_t)d * d * 8, st)); ot.Vt = bVtt.as<double>(); }  // Vt' of D' is d x M -> U = Vt''
+    MatSrc src{bDt.as<double>(), N};
+    CKR(rpca_core(h, src, false, N, M, p, ot));
+    if (o.A) CK(launch_transpose(ot.A, N, M, o.A, st, &h->launches));
+    if (o.E) CK(launch_transpose(ot.E, N, M, o.E, st, &h->launches));
+    if (o.Vt) CK(launch_transpose(ot.U, N, d, o.Vt, st, &h->launches));
+    if (o.U) CK(launch_transpose(ot.Vt, d, M, o.U, st, &h->launches));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Grassmann averages core (device pointers)
+// ----------------------------------------------------------------------------------------------------------
+int rpca_ga_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0, double tol,
+                int64_t iters, double* Q, int64_t* iters_done) {
+    if (d < 1 || N < 1 || r < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: empty problem");
+    if (!X || !q0 || !Q) return set_err(TLSQ_ERR_ARG, "rpca_ga: X, q0 and Q are required");
+    if (iters < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: iters must be >= 1");
+    cudaStream_t st = h->stream;
+    const int sms = h->sm_count;
+    int64_t* L = &h->launches;
+    const size_t dn = (size_t)d * N;
+    DevBuf bX, bT, bN2, bS, bQ, bMu, bXs, bSc;
+    CK(bX.alloc(dn * 8, st)); CK(bT.alloc((size_t)(N + 1) * 8, st)); CK(bN2.alloc((size_t)N * 8, st));
+    CK(bS.alloc((size_t)N * 8, st)); CK(bQ.alloc((size_t)d * 8, st)); CK(bMu.alloc((size_t)d * 8, st));
+    CK(bXs.alloc((size_t)N * 8, st)); CK(bSc.alloc(8 * 8, st));
+    double* Xw = bX.as<double>(); double* t = bT.as<double>(); double* n2 = bN2.as<double>();
+    double* s = bS.as<double>(); double* q = bQ.as<double>(); double* mu = bMu.as<double>();
+    double* xs = bXs.as<double>(); double* sc = bSc.as<double>();   // sc[0] = sumw, sc[1] = ss, sc[2] = dq2
+    double* hp = h->h_pin;
+    CK(cudaMemcpyAsync(Xw, X, dn * 8, cudaMemcpyDeviceToDevice, st));                    // X = copy(X)   :257
+
+    for (int64_t i = 0; i < r; ++i) {                                                    // :263
+        CK(cudaMemsetAsync(n2, 0, (size_t)N * 8, st));
+        CK(launch_ga_sweep(GA_NORMS, Xw, d, N, d, nullptr, nullptr, nullptr, n2, sms, st, L));   // :265
+        CKR(allreduce(h, n2, (size_t)N, kNcclSum));
+        // q = randn(d); q ./= norm(q)   (:286-287) -- the draw comes from the caller
+        CK(cudaMemsetAsync(sc, 0, 8 * 8, st));
+        CK(launch_vec_sumsq(q0 + i * d, d, sc + 1, sms, st, L));
+        CKR(allreduce(h, sc + 1, 1, kNcclSum));
+        CK(launch_vec_scale_rsqrt(q0 + i * d, sc + 1, d, q, sms, st, L));
+        CK(cudaMemsetAsync(t, 0, (size_t)(N + 1) * 8, st));
+        CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, q, nullptr, nullptr, t, sms, st, L));   // first U[:,n]'q  :292
+        CKR(allreduce(h, t, (size_t)N, kNcclSum));
+        int64_t its = 0;
+        for (int64_t it = 1; it <= iters; ++it) {                                        // :290
+            CK(launch_ga_signs(t, n2, N, s, sc, st, L));
+            CK(cudaMemsetAsync(t, 0, (size_t)(N + 1) * 8, st));
+            CK(launch_ga_sweep(GA_PASS, Xw, d, N, d, mu, s, sc, t, sms, st, L));         // :291-294 in one sweep
+            CKR(allreduce(h, t, (size_t)(N + 1), kNcclSum));
+            CK(cudaMemsetAsync(sc + 2, 0, 8, st));
+            CK(launch_ga_update(mu, t + N, d, q, sc + 2, sms, st, L));                   // :295-296, 302
+            CKR(allreduce(h, sc + 2, 1, kNcclSum));
+            CK(cudaMemcpyAsync(hp, sc + 2, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            its = it;
+            if (sqrt(hp[0]) < tol) break;                                                // :298
+        }
+        if (iters_done) iters_done[i] = its;
+        CK(cudaMemcpyAsync(Q + i * d, q, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));  // :269
+        CK(cudaMemsetAsync(xs, 0, (size_t)N * 8, st));
+        CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, q, nullptr, nullptr, xs, sms, st, L));  // Xs1 = q'X   :271
+        CKR(allreduce(h, xs, (size_t)N, kNcclSum));
+        CK(launch_ga_deflate(Xw, d, N, d, q, xs, sms, st, L));                           // :272
+    }
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// lowrankfilter core (device pointers)
+// ----------------------------------------------------------------------------------------------------------
+int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, int64_t lag, RpcaParams p,
+                      double* yf, int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist) {
+    if (!y || !yf) return set_err(TLSQ_ERR_ARG, "lowrankfilter: y and yf are required");
+    if (Ns < 2 || n < 1 || lag < 1) return set_err(TLSQ_ERR_ARG, "lowrankfilter: bad sizes");
+    if ((double)n > (double)Ns / 2.0)                                                    // @assert L <= N/2   :79
+        return set_err(TLSQ_ERR_ARG, "L has to be less than N/2 = %g", (double)Ns / 2.0);
+    if (lag > n) return set_err(TLSQ_ERR_ARG, "lag must be <= L");                       // :80
+    if (h->nranks > 1)
+        return set_err(TLSQ_ERR_UNSUPPORTED, "lowrankfilter: sharded signals are not implemented yet");
+    const int64_t K = (Ns - n) / lag + 1;                                                // :81
+    if (!(p.lambda > 0.0)) p.lambda = 1.0 / sqrt((double)(K > n ? K : n));               // :157
+    cudaStream_t st = h->stream;
+    DevBuf bA, bH;
+    CK(bA.alloc((size_t)K * n * 8, st));
+    RpcaOut o;
+    o.A = bA.as<double>(); o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
+    if (K >= n) {
+        if (n > kEigMaxN)
+            return set_err(TLSQ_ERR_UNSUPPORTED, "lowrankfilter: n = %lld exceeds the supported %d", (long long)n,
+                           kEigMaxN);
+        CKR(check_rpca_args(K, n, p));
+        MatSrc src{y, lag};                    // implicit Hankel: H[k,l] = y[k*lag + l], never materialised
+        CKR(rpca_core(h, src, true, K, n, p, o));
+    } else {
+        CK(bH.alloc((size_t)K * n * 8, st));
+        CK(launch_hankel(y, K, n, lag, bH.as<double>(), st, &h->launches));
+        CKR(rpca_dev(h, bH.as<double>(), K, n, p, o));
+    }
+    CK(launch_unhankel(o.A, K, n, lag, Ns, yf, st, &h->launches));                       // :127
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int tlsq_abi_version(void) { return TLSQ_ABI_VERSION; }
+const char* tlsq_last_error(void) { return g_err; }
+
+int tlsq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tlsq_create(int device, tlsq_handle** out) {
+    if (!out) return set_err(TLSQ_ERR_ARG, "tlsq_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_err(TLSQ_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return set_err(TLSQ_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_err(TLSQ_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    tlsq_handle* h = new tlsq_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double)));
+    // keep freed blocks cached in the stream-ordered pool between solves
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = h;
+    return TLSQ_OK;
+}
+
+int tlsq_destroy(tlsq_handle* h) {
+    if (!h) return TLSQ_OK;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    delete h;
+    return TLSQ_OK;
+}
+
+int tlsq_set_stream(tlsq_handle* h, void* cuda_stream) {
+    if (!h) return set_err(TLSQ_ERR_ARG, "null handle");
+    h->stream = (cudaStream_t)cuda_stream;
+    return TLSQ_OK;
+}
+
+int tlsq_use_own_stream(tlsq_handle* h) {
+    if (!h) return set_err(TLSQ_ERR_ARG, "null handle");
+    h->stream = h->own_stream;
+    return TLSQ_OK;
+}
+
+int64_t tlsq_launch_count(const tlsq_handle* h) { return h ? h->launches : 0; }
+
+int tlsq_comm_unique_id(void* id128) {
+    if (!id128) return set_err(TLSQ_ERR_ARG, "id128 is NULL");
+    CKR(nccl_load());
+    NcclId id;
+    int r = g_nccl.get_uid(&id);
+    if (r != 0) return set_err(TLSQ_ERR_NCCL, "ncclGetUniqueId failed: %s", g_nccl.errstr ? g_nccl.errstr(r) : "?");
+    memcpy(id128, &id, 128);
+    return TLSQ_OK;
+}
+
+int tlsq_comm_init(tlsq_handle* h, int nranks, int rank, const void* id128) {
+    CKR(use_device(h));
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return set_err(TLSQ_ERR_ARG, "bad communicator args");
+    if (nranks == 1) { h->nranks = 1; h->rank = 0; return TLSQ_OK; }
+    CKR(nccl_load());
+    NcclId id;
+    memcpy(&id, id128, 128);
+    int r = g_nccl.init_rank(&h->comm, nranks, id, rank);
+    if (r != 0) return set_err(TLSQ_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.errstr ? g_nccl.errstr(r) : "?");
+    h->nranks = nranks;
+    h->rank = rank;
+    return TLSQ_OK;
+}
+
+// ---- rpca ------------------------------------------------------------------------------------------------
+int tlsq_rpca_f64_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, double lambda, int64_t maxrank,
+                      int64_t iters, double tol, double rho, uint32_t flags, double* A, double* E, double* U,
+                      double* S, double* Vt, int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist) {
+    CKR(use_device(h));
+    if (!D) return set_err(TLSQ_ERR_ARG, "rpca: D is NULL");
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    RpcaOut o;
+    o.A = A; o.E = E; o.U = U; o.S = S; o.Vt = Vt; o.sv = sv; o.iters_done = iters_done; o.converged = converged;
+    o.hist = hist;
+    return rpca_dev(h, D, M, N, p, o);
+}
+
+int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double lambda, int64_t maxrank,
+                  int64_t iters, double tol, double rho, uint32_t flags, double* A, double* E, double* U, double* S,
+                  double* Vt, int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist) {
+    CKR(use_device(h));
+    if (!D) return set_err(TLSQ_ERR_ARG, "rpca: D is NULL");
+    if (M < 1 || N < 1) return set_err(TLSQ_ERR_ARG, "rpca: empty matrix");
+    cudaStream_t st = h->stream;
+    const size_t mn = (size_t)M * N;
+    const int64_t d = M < N ? M : N;      // (sharded callers use the _dev entry; here M is the full row count)
+    DevBuf bD, bA, bE, bU, bS, bVt;
+    CK(bD.alloc(mn * 8, st));
+    CK(cudaMemcpyAsync(bD.as<double>(), D, mn * 8, cudaMemcpyHostToDevice, st));
+    if (A) CK(bA.alloc(mn * 8, st));
+    if (E) CK(bE.alloc(mn * 8, st));
+    if (U) CK(bU.alloc((size_t)M * d * 8, st));
+    if (S) CK(bS.alloc((size_t)d * 8, st));
+    if (Vt) CK(bVt.alloc((size_t)d * N * 8, st));
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    RpcaOut o;
+    o.A = A ? bA.as<double>() : nullptr; o.E = E ? bE.as<double>() : nullptr; o.U = U ? bU.as<double>() : nullptr;
+    o.S = S ? bS.as<double>() : nullptr; o.Vt = Vt ? bVt.as<double>() : nullptr;
+    o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
+    CKR(rpca_dev(h, bD.as<double>(), M, N, p, o));
+    if (A) CK(cudaMemcpyAsync(A, o.A, mn * 8, cudaMemcpyDeviceToHost, st));
+    if (E) CK(cudaMemcpyAsync(E, o.E, mn * 8, cudaMemcpyDeviceToHost, st));
+    if (U) CK(cudaMemcpyAsync(U, o.U, (size_t)M * d * 8, cudaMemcpyDeviceToHost, st));
+    if (S) CK(cudaMemcpyAsync(S, o.S, (size_t)d * 8, cudaMemcpyDeviceToHost, st));
+    if (Vt) CK(cudaMemcpyAsync(Vt, o.Vt, (size_t)d * N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ---- lowrankfilter ---------------------------------------------------------------------------------------
+int tlsq_lowrankfilter_f64_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, int64_t lag, double lambda,
+                               int64_t maxrank, int64_t iters, double tol, double rho, uint32_t flags, double* yf,
+                               int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist) {
+    CKR(use_device(h));
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    return lowrankfilter_dev(h, y, Ns, n, lag, p, yf, sv, iters_done, converged, hist);
+}
+
+int tlsq_lowrankfilter_f64(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, int64_t lag, double lambda,
+                           int64_t maxrank, int64_t iters, double tol, double rho, uint32_t flags, double* yf,
+                           int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist) {
+    CKR(use_device(h));
+    if (!y || !yf || Ns < 1) return set_err(TLSQ_ERR_ARG, "lowrankfilter: y and yf are required");
+    cudaStream_t st = h->stream;
+    DevBuf by, bf;
+    CK(by.alloc((size_t)Ns * 8, st)); CK(bf.alloc((size_t)Ns * 8, st));
+    CK(cudaMemcpyAsync(by.as<double>(), y, (size_t)Ns * 8, cudaMemcpyHostToDevice, st));
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    CKR(lowrankfilter_dev(h, by.as<double>(), Ns, n, lag, p, bf.as<double>(), sv, iters_done, converged, hist));
+    CK(cudaMemcpyAsync(yf, bf.as<double>(), (size_t)Ns * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ---- rpca_ga ---------------------------------------------------------------------------------------------
+int tlsq_rpca_ga_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0,
+                         double tol, int64_t iters, double* Q, int64_t* iters_done) {
+    CKR(use_device(h));
+    return rpca_ga_dev(h, X, d, N, r, q0, tol, iters, Q, iters_done);
+}
+
+int tlsq_rpca_ga_f64(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0, double tol,
+                     int64_t iters, double* Q, int64_t* iters_done) {
+    CKR(use_device(h));
+    if (!X || !q0 || !Q || d < 1 || N < 1 || r < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: bad arguments");
+    cudaStream_t st = h->stream;
+    DevBuf bX, bq0, bQ;
+    CK(bX.alloc((size_t)d * N * 8, st)); CK(bq0.alloc((size_t)d * r * 8, st)); CK(bQ.alloc((size_t)d * r * 8, st));
+    CK(cudaMemcpyAsync(bX.as<double>(), X, (size_t)d * N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(bq0.as<double>(), q0, (size_t)d * r * 8, cudaMemcpyHostToDevice, st));
+    CKR(rpca_ga_dev(h, bX.as<double>(), d, N, r, bq0.as<double>(), tol, iters, bQ.as<double>(), iters_done));
+    CK(cudaMemcpyAsync(Q, bQ.as<double>(), (size_t)d * r * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ---- hankel / unhankel -----------------------------------------------------------------------------------
+int tlsq_hankel_f64(tlsq_handle* h, const double* x, int64_t Ns, int64_t L, int64_t lag, double* H) {
+    CKR(use_device(h));
+    if (!x || !H || Ns < 1 || L < 1 || lag < 1) return set_err(TLSQ_ERR_ARG, "hankel: bad arguments");
+    if ((double)L > (double)Ns / 2.0) return set_err(TLSQ_ERR_ARG, "L has to be less than N/2 = %g", (double)Ns / 2.0);
+    if (lag > L) return set_err(TLSQ_ERR_ARG, "lag must be <= L");
+    const int64_t K = (Ns - L) / lag + 1;
+    cudaStream_t st = h->stream;
+    DevBuf bx, bH;
+    CK(bx.alloc((size_t)Ns * 8, st)); CK(bH.alloc((size_t)K * L * 8, st));
+    CK(cudaMemcpyAsync(bx.as<double>(), x, (size_t)Ns * 8, cudaMemcpyHostToDevice, st));
+    CK(launch_hankel(bx.as<double>(), K, L, lag, bH.as<double>(), st, &h->launches));
+    CK(cudaMemcpyAsync(H, bH.as<double>(), (size_t)K * L * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+int tlsq_unhankel_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, double* y) {
+    CKR(use_device(h));
+    if (!A || !y || K < 1 || L < 1 || lag < 1 || Ns < 1) return set_err(TLSQ_ERR_ARG, "unhankel: bad arguments");
+    cudaStream_t st = h->stream;
+    DevBuf bA, by;
+    CK(bA.alloc((size_t)K * L * 8, st)); CK(by.alloc((size_t)Ns * 8, st));
+    CK(cudaMemcpyAsync(bA.as<double>(), A, (size_t)K * L * 8, cudaMemcpyHostToDevice, st));
+    CK(launch_unhankel(bA.as<double>(), K, L, lag, Ns, by.as<double>(), st, &h->launches));
+    CK(cudaMemcpyAsync(y, by.as<double>(), (size_t)Ns * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ---- building blocks -------------------------------------------------------------------------------------
+int tlsq_gram_f64_dev(tlsq_handle* h, const double* X, int64_t M, int64_t n, double* G) {
+    CKR(use_device(h));
+    if (!X || !G || M < 1 || n < 1) return set_err(TLSQ_ERR_ARG, "gram: bad arguments");
+    cudaStream_t st = h->stream;
+    GramPlan plan = gram_plan(M, n, h->sm_count);
+    DevBuf bP;
+    CK(bP.alloc(plan.partial_bytes, st));
+    GramSrc gs;
+    gs.D = MatSrc{X, M}; gs.A = nullptr; gs.Y = nullptr; gs.A2 = nullptr; gs.ldw = M; gs.M = M; gs.N = n;
+    gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = 0;
+    CK(launch_gram(gs, GRAM_D, false, plan, bP.as<double>(), G, st, &h->launches));
+    CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+int tlsq_eigh_f64_dev(tlsq_handle* h, const double* G, int64_t n, double* lam, double* V) {
+    CKR(use_device(h));
+    if (!G || !lam || !V || n < 1) return set_err(TLSQ_ERR_ARG, "eigh: bad arguments");
+    if (n > kEigMaxN) return set_err(TLSQ_ERR_UNSUPPORTED, "eigh: n = %lld exceeds %d", (long long)n, kEigMaxN);
+    cudaStream_t st = h->stream;
+    DevBuf bE;
+    CK(bE.alloc(eig_work_doubles((int)n) * 8, st));
+    EigWork ew;
+    double* base = bE.as<double>();
+    const size_t np = (size_t)n + 34;
+    ew.X0 = base; base += (size_t)n * n;
+    ew.Xo = base; base += np * n;
+    ew.Vo = base; base += np * n;
+    ew.lam_raw = base; base += np;
+    ew.perm = reinterpret_cast<int*>(base); base += n;
+    ew.info = reinterpret_cast<int*>(base);
+    CK(launch_eigh(G, (int)n, nullptr, ew, lam, V, h->sm_count, st, &h->launches));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+}  // extern "C"
