@@ -69,6 +69,20 @@ int         tlsq_use_own_stream(tlsq_handle* h);
 /* number of kernels launched through this handle since creation (bench.py's gpu_launches) */
 int64_t     tlsq_launch_count(const tlsq_handle* h);
 
+/* optional device-side phase timing (CUDA events on the solve stream; off by default).  tlsq_set_profiling resets
+ * the accumulators; tlsq_get_profile returns accumulated milliseconds and span counts per phase. */
+#define TLSQ_NUM_PHASES        8
+#define TLSQ_PHASE_GRAM        0   /* DMMA Gram of the SVT input (+ deterministic reduce)            */
+#define TLSQ_PHASE_EIG         1   /* n x n Jacobi eigensolver (+ warm-start GEMM, sort, shrink)     */
+#define TLSQ_PHASE_EPILOGUE    2   /* fused E / W / A / Z / Y pass                                    */
+#define TLSQ_PHASE_EXACT_COST  3   /* Gram of Z + eigensolver when the Frobenius bracket is undecided */
+#define TLSQ_PHASE_INIT        4   /* opnorm(D), max|D|, Y = D/dual                                   */
+#define TLSQ_PHASE_FINALIZE    5   /* E, U, S, Vt outputs                                             */
+#define TLSQ_PHASE_ALLREDUCE   6   /* NCCL all-reduces                                                */
+#define TLSQ_PHASE_GA_SWEEP    7   /* Grassmann-average streaming sweep                               */
+int tlsq_set_profiling(tlsq_handle* h, int on);
+int tlsq_get_profile(tlsq_handle* h, double* ms, int64_t* calls);
+
 /* ---- multi-GPU (row-sharded) ------------------------------------------------------------------------------ */
 /* fill a 128-byte NCCL unique id (rank 0 calls this and broadcasts the bytes to the other ranks) */
 int tlsq_comm_unique_id(void* id128);

@@ -22,11 +22,11 @@ from typing import NamedTuple, Optional
 
 import numpy as np
 
-from . import _cabi
+from . import _cabi, synth  # noqa: F401
 from ._cabi import TlsqError, load  # noqa: F401
 
 __all__ = ["rpca", "rpca_ga", "lowrankfilter", "hankel", "unhankel", "SVD", "TlsqError", "get_handle",
-           "init_distributed", "launch_count", "gram", "eigh"]
+           "init_distributed", "launch_count", "gram", "eigh", "set_profiling", "get_profile", "PHASES"]
 
 
 class SVD(NamedTuple):
@@ -73,6 +73,22 @@ def _default_device() -> int:
 def launch_count(device: Optional[int] = None) -> int:
     """Number of CUDA kernels this process launched through the handle (bench.py's gpu_launches)."""
     return int(load().tlsq_launch_count(get_handle(device)))
+
+
+PHASES = ("gram", "eig", "epilogue", "exact_cost", "init", "finalize", "allreduce", "ga_sweep")
+
+
+def set_profiling(on: bool, device: Optional[int] = None) -> None:
+    """Switch the library's per-phase CUDA-event timing on/off (resets the accumulators)."""
+    _cabi.check(load().tlsq_set_profiling(get_handle(device), 1 if on else 0))
+
+
+def get_profile(device: Optional[int] = None) -> dict:
+    """{phase: (milliseconds, spans)} accumulated since set_profiling(True)."""
+    ms = (C.c_double * 8)()
+    calls = (C.c_int64 * 8)()
+    _cabi.check(load().tlsq_get_profile(get_handle(device), ms, calls))
+    return {name: (float(ms[i]), int(calls[i])) for i, name in enumerate(PHASES)}
 
 
 def init_distributed(device: Optional[int] = None) -> None:
@@ -181,7 +197,7 @@ def rpca(D, *, lam: Optional[float] = None, maxrank: Optional[int] = None, iters
          tol: Optional[float] = None, rho: float = 1.5, verbose: bool = False, nonnegA: bool = False,
          nonnegE: bool = False, hankel: bool = False, nukeA: bool = True, svd=None, opnorm=None,
          return_info: bool = False, want_svd: bool = True, want_E: bool = True, exact_cost: bool = False,
-         **kwargs):
+         out=None, **kwargs):
     """``A, E, s, sv = rpca(D; lam, maxrank, iters, tol, rho, verbose, nonnegA, nonnegE, hankel, nukeA)``.
 
     Drop-in for src/robustPCA.jl:156-239 (``lam`` is the reference's ``λ``, ``rho`` its ``ρ``; the Greek names are
@@ -209,8 +225,17 @@ def rpca(D, *, lam: Optional[float] = None, maxrank: Optional[int] = None, iters
             (_cabi.TLSQ_HANKEL if hankel else 0) | (0 if nukeA else _cabi.TLSQ_NO_NUKE_A) | \
             (_cabi.TLSQ_EXACT_COST if (verbose or exact_cost) else 0)
     h = _handle_for(Da)
-    A, pA = _empty_like(Da, (M, N))
-    E, pE = _empty_like(Da, (M, N)) if want_E else (None, None)
+    if out is not None:                      # caller-provided (e.g. pinned) column-major outputs (A, E)
+        Ao, Eo = _Arr(out[0], "out[0]"), (_Arr(out[1], "out[1]") if out[1] is not None else None)
+        if Ao.obj is not out[0] or tuple(Ao.shape) != (M, N) or Ao.torch != Da.torch:
+            raise ValueError("rpca: out[0] must be a column-major float64 M x N array of the same kind as D")
+        A, pA = Ao.obj, Ao.ptr
+        E, pE = (Eo.obj, Eo.ptr) if Eo is not None else (None, None)
+        if Eo is not None and (Eo.obj is not out[1] or tuple(Eo.shape) != (M, N)):
+            raise ValueError("rpca: out[1] must be a column-major float64 M x N array")
+    else:
+        A, pA = _empty_like(Da, (M, N))
+        E, pE = _empty_like(Da, (M, N)) if want_E else (None, None)
     if want_svd:
         U, pU = _empty_like(Da, (M, d))
         S, pS = _empty_like(Da, (d,))

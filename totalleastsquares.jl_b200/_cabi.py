@@ -31,6 +31,8 @@ SIGNATURES = {
     "tlsq_set_stream": (C.c_int, [vp, vp]),
     "tlsq_use_own_stream": (C.c_int, [vp]),
     "tlsq_launch_count": (C.c_int64, [vp]),
+    "tlsq_set_profiling": (C.c_int, [vp, C.c_int]),
+    "tlsq_get_profile": (C.c_int, [vp, c_dp, c_i64p]),
     "tlsq_comm_unique_id": (C.c_int, [vp]),
     "tlsq_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "tlsq_rpca_f64": (C.c_int, _RPCA_ARGS),

@@ -119,17 +119,17 @@ gram_kernel(const GramSrc s, double* __restrict__ partial, int nb, int ntiles) {
 }
 
 // G[i,j] = G[j,i] = sum_split partial[split][blk(i,j)][jl][il]   for i <= j  (fixed summation order)
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nsplit, int nblk, int nb, int N,
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nsplit, int nblk, int nb, int B, int N,
                                    double* __restrict__ G) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * N) return;
     const int i = (int)(idx % N), j = (int)(idx / N);
     if (i > j) return;
-    const int bi = i / GB, bj = j / GB, il = i % GB, jl = j % GB;
+    const int bi = i / B, bj = j / B, il = i % B, jl = j % B;
     const int blk = bi * nb - (bi * (bi - 1)) / 2 + (bj - bi);
-    const double* p = partial + (int64_t)blk * (GB * GB) + jl * GB + il;
+    const double* p = partial + (int64_t)blk * (B * B) + jl * B + il;
     double sum = 0.0;
-    for (int sp = 0; sp < nsplit; ++sp) sum += p[(int64_t)sp * nblk * (GB * GB)];
+    for (int sp = 0; sp < nsplit; ++sp) sum += p[(int64_t)sp * nblk * (B * B)];
     G[(int64_t)j * N + i] = sum;
     G[(int64_t)i * N + j] = sum;
 }
@@ -170,10 +170,14 @@ cudaError_t launch_gram(const GramSrc& s, GramMode mode, bool hankel, const Gram
         default:     e = launch_mode<GRAM_Z>(s, hankel, plan, partial, st); break;
     }
     if (e != cudaSuccess) return e;
-    const int64_t nn = s.N * s.N;
-    gram_reduce_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(partial, plan.nsplit, plan.nblk, plan.nb,
-                                                                     (int)s.N, G);
     if (launches) *launches += 2;
+    return launch_gram_reduce(partial, plan.nsplit, plan.nblk, plan.nb, GB, (int)s.N, G, st);
+}
+
+cudaError_t launch_gram_reduce(const double* partial, int nsplit, int nblk, int nb, int B, int N, double* G,
+                               cudaStream_t st) {
+    const int64_t nn = (int64_t)N * N;
+    gram_reduce_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(partial, nsplit, nblk, nb, B, N, G);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,18 @@ GramPlan gram_plan(int64_t M, int64_t N, int sm_count);
 cudaError_t launch_gram(const GramSrc& s, GramMode mode, bool hankel, const GramPlan& plan, double* partial,
                         double* G, cudaStream_t st, int64_t* launches);
 
+cudaError_t launch_gram_reduce(const double* partial, int nsplit, int nblk, int nb, int B, int N, double* G,
+                               cudaStream_t st);
+
+// TMA-fed SYRK for a materialised dense X (syrk_tma.cu): 128 x 128 blocks, 16-row boxes, 4-stage mbarrier ring
+constexpr int kSyrkBlk = 128;
+constexpr int kEigMaxN = 512;
+struct SyrkPlan { int nb; int nblk; int nsplit; int ntiles; size_t partial_bytes; };
+bool syrk_tma_eligible(const double* X, int64_t M, int64_t N, int64_t ld);
+SyrkPlan syrk_plan(int64_t M, int64_t N, int sm_count);
+cudaError_t launch_syrk_tma(const double* X, int64_t M, int64_t N, int64_t ld, const SyrkPlan& plan, double* partial,
+                            double* G, cudaStream_t st, int64_t* launches);
+
 // ----------------------------------------------------------------------------------------------------
 // Small symmetric eigenproblem (n <= 512): one-sided Jacobi with warp-shuffle rotations.
 // ----------------------------------------------------------------------------------------------------
@@ -48,7 +60,6 @@ struct EigWork {       // all device pointers, sized for n (see eig_work_bytes)
     int*    info;      // [0] sweeps done, [1] rotations in last sweep, [2..] per-sweep counters (64)
 };
 size_t eig_work_doubles(int n);
-constexpr int kEigMaxN = 512;
 // Eigen-decomposition of symmetric PSD G (n x n, ld n).  If V0 != nullptr it must hold an orthogonal n x n
 // warm-start basis (previous eigenvectors).  Outputs: lam (n, descending), Vs (n x n sorted eigenvector columns).
 // Vs may alias V0.
@@ -70,6 +81,8 @@ struct EpiArgs {
     double* An;         // A_k      (may alias Ap: the pass is tile-local)
     double* Yn;         // Y_k      (may alias Yp)
     double* Eout;       // optional E_k
+    double* Wn;         // optional W_{k+1} = D - E_{k+1} + Y_k/mu_{k+1} (materialised SVT input of the next iteration)
+    double im_next, eps_next;   // 1/mu_{k+1}, lambda/mu_{k+1}
     double* Uout;       // MODE U only: M x d
     int64_t M, N, ldw;
     const double* Vs;   // N x N sorted right singular vectors (ld N)
@@ -86,8 +99,10 @@ cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_c
 // maxabs: *out = max |D_ij| (out must be zeroed);  init: Y = D / dual, A = 0
 cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, double* out, int sm_count,
                           cudaStream_t st, int64_t* launches);
+// W (optional) = SVT input of the first iteration: (D - E_1) + Y_0/mu_1 with A_0 = 0
 cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A,
-                           int sm_count, cudaStream_t st, int64_t* launches);
+                           double* W, double im, double eps, int nonnegE, int sm_count, cudaStream_t st,
+                           int64_t* launches);
 // E = soft_th((D - A) + Y/mu, lambda/mu) (+ clamp)
 cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N, const double* A, const double* Y,
                              double im, double eps, int nonnegE, double* E, int sm_count, cudaStream_t st,

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -110,6 +111,14 @@ struct tlsq_handle {
     int nranks = 1;
     int rank = 0;
     double* h_pin = nullptr;     // pinned host scratch (64 doubles)
+    // optional per-phase device timing (CUDA events on the solve stream)
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int phase; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double phase_ms[TLSQ_NUM_PHASES] = {0};
+    int64_t phase_calls[TLSQ_NUM_PHASES] = {0};
 };
 
 namespace {
@@ -129,8 +138,47 @@ struct DevBuf {                  // stream-ordered device allocation, freed on s
     DevBuf& operator=(const DevBuf&) = delete;
 };
 
+cudaEvent_t prof_event(tlsq_handle* h) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[h->ev_used++];
+}
+
+struct Phase {                   // RAII span: records start/stop events on the solve stream when profiling is on
+    tlsq_handle* h;
+    int phase;
+    cudaEvent_t a = nullptr;
+    Phase(tlsq_handle* hh, int ph) : h(hh), phase(ph) {
+        if (h->prof) { a = prof_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~Phase() {
+        if (h->prof && a) {
+            cudaEvent_t b = prof_event(h);
+            cudaEventRecord(b, h->stream);
+            h->spans.push_back({phase, a, b});
+        }
+    }
+};
+
+void prof_collect(tlsq_handle* h) {      // call after the stream was synchronised
+    if (!h->prof) return;
+    for (auto& sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            h->phase_ms[sp.phase] += ms;
+            h->phase_calls[sp.phase] += 1;
+        }
+    }
+    h->spans.clear();
+    h->ev_used = 0;
+}
+
 int allreduce(tlsq_handle* h, double* buf, size_t count, int op) {
     if (h->nranks <= 1) return TLSQ_OK;
+    Phase ph(h, TLSQ_PHASE_ALLREDUCE);
     int r = g_nccl.allreduce(buf, buf, count, kNcclFloat64, op, h->comm, h->stream);
     if (r != 0) return set_err(TLSQ_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(r) : "?");
     return TLSQ_OK;
@@ -170,6 +218,15 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // global row count (for the Frobenius bracket: d = min(M_global, N))
     double Mg = (double)M;
     GramPlan plan = gram_plan(M, N, sms);
+    // Fast path: the SVT input W_k is materialised by the previous epilogue and its Gram runs on the TMA-fed
+    // DMMA SYRK kernel (needs an even leading dimension for the 16-byte TMA stride and a tall enough matrix).
+    const bool use_w = syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), M, N, M);
+    SyrkPlan splan = syrk_plan(M, N, sms);
+    const size_t part_bytes = use_w && splan.partial_bytes > plan.partial_bytes ? splan.partial_bytes
+                                                                                 : plan.partial_bytes;
+    DevBuf bW;
+    if (use_w) CK(bW.alloc(mn * 8, st));
+    double* Wbuf = use_w ? bW.as<double>() : nullptr;
 
     DevBuf bA0, bA1, bY0, bY1, bPart, bG, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
     // A ping-pong: reuse the caller's A buffer as one side when given
@@ -178,7 +235,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     CK(bA1.alloc(mn * 8, st)); Abuf[1] = bA1.as<double>();
     CK(bY0.alloc(mn * 8, st)); CK(bY1.alloc(mn * 8, st));
     double* Ybuf[2] = {bY0.as<double>(), bY1.as<double>()};
-    CK(bPart.alloc(plan.partial_bytes, st));
+    CK(bPart.alloc(part_bytes, st));
     CK(bG.alloc((size_t)n * n * 8, st)); CK(bG2.alloc((size_t)n * n * 8, st));
     CK(bVs.alloc((size_t)n * n * 8, st)); CK(bVs2.alloc((size_t)n * n * 8, st));
     CK(bLam.alloc((size_t)n * 8, st)); CK(bLam2.alloc((size_t)n * 8, st));
@@ -219,11 +276,17 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     GramSrc gs;
     gs.D = D; gs.A = nullptr; gs.Y = nullptr; gs.A2 = nullptr; gs.ldw = M; gs.M = M; gs.N = N;
     gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = nonnegE;
-    CK(launch_gram(gs, GRAM_D, hankel, plan, bPart.as<double>(), G, st, L));            // D'D
-    CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
-    CK(launch_maxabs(D, hankel, M, N, dscal + 1, sms, st, L));                           // norm(Y, Inf)   :178
-    CKR(allreduce(h, dscal + 1, 1, kNcclMax));
-    CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));                             // opnorm(Y)      :177
+    {
+        Phase ph(h, TLSQ_PHASE_INIT);
+        if (use_w && !hankel && syrk_tma_eligible(D.p, M, N, D.ld))
+            CK(launch_syrk_tma(D.p, M, N, D.ld, splan, bPart.as<double>(), G, st, L));   // D'D
+        else
+            CK(launch_gram(gs, GRAM_D, hankel, plan, bPart.as<double>(), G, st, L));
+        CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+        CK(launch_maxabs(D, hankel, M, N, dscal + 1, sms, st, L));                       // norm(Y, Inf)   :178
+        CKR(allreduce(h, dscal + 1, 1, kNcclMax));
+        CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));                         // opnorm(Y)      :177
+    }
     CK(cudaMemcpyAsync(hp, lam, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hp + 1, dscal + 1, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -233,7 +296,11 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     const double d_norm = norm2;                                                         // :180
     double mu = 1.25 / norm2;                                                            // :182
     const double mubar = mu * 1.0e7;                                                     // :183
-    CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], Abuf[0], sms, st, L));        // Y ./= dual_norm :181
+    {
+        Phase ph(h, TLSQ_PHASE_INIT);
+        CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], Abuf[0], Wbuf, 1.0 / mu, p.lambda / mu, nonnegE,
+                          sms, st, L));                                                  // Y ./= dual_norm :181
+    }
 
     int cur = 0;
     int64_t k_done = 0;
@@ -248,10 +315,17 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         const double eps = p.lambda / mu;
         // SVT input Gram  (:188-194)
         gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = nullptr; gs.im = im; gs.eps = eps;
-        CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+        {
+            Phase ph(h, TLSQ_PHASE_GRAM);
+            if (use_w) CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), G, st, L));
+            else CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+        }
         CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
-        CK(launch_eigh(G, n, Vs, ew, lam, Vs, sms, st, L));                              // warm start from V_{k-1}
-        CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L));                // :198
+        {
+            Phase ph(h, TLSQ_PHASE_EIG);
+            CK(launch_eigh(G, n, Vs, ew, lam, Vs, sms, st, L));                          // warm start from V_{k-1}
+            CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L));            // :198
+        }
         // fused epilogue  (:188-192, 205-222)
         CK(cudaMemsetAsync(dscal, 0, 8, st));
         EpiArgs ea;
@@ -259,17 +333,29 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
         ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
         ea.zz = dscal;
-        CK(launch_epilogue(ea, hankel, false, sms, st, L));
+        const double mu_next = fmin(mu * p.rho, mubar);                                  // :223
+        ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
+        {
+            Phase ph(h, TLSQ_PHASE_EPILOGUE);
+            CK(launch_epilogue(ea, hankel, false, sms, st, L));
+        }
         CKR(allreduce(h, dscal, 1, kNcclSum));
         CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
+        static const bool dbg_eig = getenv("TLSQ_DEBUG_EIG") != nullptr;
+        if (dbg_eig) CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (dbg_eig) {
+            int sw;
+            memcpy(&sw, hp + 2, 4);
+            fprintf(stderr, "[tlsq] iter %lld: jacobi sweeps %d\n", (long long)k, sw);
+        }
         const double zz = hp[0];
         int svp;
         memcpy(&svp, hp + 1, 4);
         svp_last = svp;
         im_last = im; eps_last = eps; prev_idx = cur; last_idx = nxt;
-        mu = fmin(mu * p.rho, mubar);                                                    // :223
+        mu = mu_next;
         // stop test  cost = opnorm(Z)/d_norm < tol   (:225-231)
         const double fro = sqrt(zz) / d_norm;        // ||Z||_F/d_norm >= cost >= ||Z||_F/(sqrt(d) d_norm)
         double cost_rec = -fro;
@@ -281,6 +367,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             else need_exact = true;
         }
         if (need_exact) {
+            Phase ph(h, TLSQ_PHASE_EXACT_COST);
             gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;
             CK(launch_gram(gs, GRAM_Z, hankel, plan, bPart.as<double>(), G2, st, L));
             CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
@@ -302,6 +389,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     }
 
     // ---- outputs (:238) ----------------------------------------------------------------------------------
+    Phase ph_final(h, TLSQ_PHASE_FINALIZE);
     // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
     // produced before A_k is copied there.
     if (o.E)
@@ -319,6 +407,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
         EpiArgs ea;
         ea.D = D; ea.Ap = Abuf[prev_idx]; ea.Yp = Ybuf[prev_idx]; ea.An = nullptr; ea.Yn = nullptr;
+        ea.Wn = nullptr; ea.im_next = 0.0; ea.eps_next = 0.0;
         ea.Eout = nullptr; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
         ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last; ea.mu = 0.0; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
         ea.zz = dscal;
@@ -422,7 +511,10 @@ int rpca_ga_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r
         for (int64_t it = 1; it <= iters; ++it) {                                        // :290
             CK(launch_ga_signs(t, n2, N, s, sc, st, L));
             CK(cudaMemsetAsync(t, 0, (size_t)(N + 1) * 8, st));
-            CK(launch_ga_sweep(GA_PASS, Xw, d, N, d, mu, s, sc, t, sms, st, L));         // :291-294 in one sweep
+            {
+                Phase ph(h, TLSQ_PHASE_GA_SWEEP);
+                CK(launch_ga_sweep(GA_PASS, Xw, d, N, d, mu, s, sc, t, sms, st, L));     // :291-294 in one sweep
+            }
             CKR(allreduce(h, t, (size_t)(N + 1), kNcclSum));
             CK(cudaMemsetAsync(sc + 2, 0, 8, st));
             CK(launch_ga_update(mu, t + N, d, q, sc + 2, sms, st, L));                   // :295-296, 302
@@ -549,6 +641,22 @@ int tlsq_use_own_stream(tlsq_handle* h) {
 }
 
 int64_t tlsq_launch_count(const tlsq_handle* h) { return h ? h->launches : 0; }
+
+int tlsq_set_profiling(tlsq_handle* h, int on) {
+    if (!h) return set_err(TLSQ_ERR_ARG, "null handle");
+    h->prof = on != 0;
+    for (int i = 0; i < TLSQ_NUM_PHASES; ++i) { h->phase_ms[i] = 0.0; h->phase_calls[i] = 0; }
+    h->spans.clear();
+    h->ev_used = 0;
+    return TLSQ_OK;
+}
+
+int tlsq_get_profile(tlsq_handle* h, double* ms, int64_t* calls) {
+    if (!h || !ms || !calls) return set_err(TLSQ_ERR_ARG, "null argument");
+    if (cudaSetDevice(h->device) == cudaSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess) prof_collect(h);
+    for (int i = 0; i < TLSQ_NUM_PHASES; ++i) { ms[i] = h->phase_ms[i]; calls[i] = h->phase_calls[i]; }
+    return TLSQ_OK;
+}
 
 int tlsq_comm_unique_id(void* id128) {
     if (!id128) return set_err(TLSQ_ERR_ARG, "id128 is NULL");
@@ -701,13 +809,19 @@ int tlsq_gram_f64_dev(tlsq_handle* h, const double* X, int64_t M, int64_t n, dou
     CKR(use_device(h));
     if (!X || !G || M < 1 || n < 1) return set_err(TLSQ_ERR_ARG, "gram: bad arguments");
     cudaStream_t st = h->stream;
-    GramPlan plan = gram_plan(M, n, h->sm_count);
     DevBuf bP;
-    CK(bP.alloc(plan.partial_bytes, st));
-    GramSrc gs;
-    gs.D = MatSrc{X, M}; gs.A = nullptr; gs.Y = nullptr; gs.A2 = nullptr; gs.ldw = M; gs.M = M; gs.N = n;
-    gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = 0;
-    CK(launch_gram(gs, GRAM_D, false, plan, bP.as<double>(), G, st, &h->launches));
+    if (syrk_tma_eligible(X, M, n, M)) {
+        SyrkPlan sp = syrk_plan(M, n, h->sm_count);
+        CK(bP.alloc(sp.partial_bytes, st));
+        CK(launch_syrk_tma(X, M, n, M, sp, bP.as<double>(), G, st, &h->launches));
+    } else {
+        GramPlan plan = gram_plan(M, n, h->sm_count);
+        CK(bP.alloc(plan.partial_bytes, st));
+        GramSrc gs;
+        gs.D = MatSrc{X, M}; gs.A = nullptr; gs.Y = nullptr; gs.A2 = nullptr; gs.ldw = M; gs.M = M; gs.N = n;
+        gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = 0;
+        CK(launch_gram(gs, GRAM_D, false, plan, bP.as<double>(), G, st, &h->launches));
+    }
     CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
     CK(cudaStreamSynchronize(st));
     return TLSQ_OK;

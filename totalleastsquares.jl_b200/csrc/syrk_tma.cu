@@ -1,0 +1,226 @@
+// syrk_tma.cu -- G = X'X for a dense, materialised tall matrix X (M x N, column-major) at FP64 tensor-core rate.
+//
+// This is the hot Gram pass of the ALM loop once the SVT input W_k is materialised by the previous epilogue
+// (replaces LAPACK dgesdd of src/robustPCA.jl:194; also used for opnorm(D), :177).  Blackwell-native data path:
+//   * TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) streams 16-row x 128-column boxes of X into a 4-stage shared
+//     memory ring, completion signalled on mbarriers (no register staging, 128 KB in flight per SM);
+//   * the boxes land with the hardware 128-byte swizzle; together with a permuted k order inside each 16-row
+//     tile (lane t takes k = 2s + (t&1) + 8(t>>1)) every 8-byte DMMA fragment load of a half-warp hits 16
+//     distinct banks -- no padding, no conflicts;
+//   * 8 warps in a 4 x 2 layout own a 128 x 128 output block, warp tile 32 x 64 = 32 DMMA.8x8x4 accumulators
+//     (64 FP64 registers pairs) per k-step, FP64 tensor pipe (mma.sync.m8n8k4.f64; tcgen05 has no FP64 kind).
+// grid.x enumerates the upper-triangular 128-blocks (bi <= bj), grid.y splits the rows; CTAs of one split stream
+// the same rows at the same time so the panels shared between blocks are served by L2.  Partial blocks are
+// summed in fixed order by gram_reduce (deterministic).
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace tlsq {
+
+namespace {
+
+constexpr int SB = kSyrkBlk;      // 128 output block edge
+constexpr int SR = 16;            // rows per TMA box / pipeline stage
+constexpr int SST = 4;            // pipeline stages
+constexpr int PANEL_BYTES = SB * SR * 8;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ partial, int nb, int ntiles) {
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ uint64_t full_bar[SST];
+    // 1024-byte alignment required by the 128B swizzle pattern
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+    int bi = 0, bj = 0;
+    {
+        int rem = blockIdx.x;
+        for (bi = 0; bi < nb; ++bi) {
+            const int cnt = nb - bi;
+            if (rem < cnt) { bj = bi + rem; break; }
+            rem -= cnt;
+        }
+    }
+    const bool diag = (bi == bj);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wi = warp & 3, wj = warp >> 2;          // warp tile rows(i) [32wi, +32), cols(j) [64wj, +64)
+    const bool active = !(diag && (32 * wi >= 64 * wj + 64));
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SST; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nmy = (ntiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;   // k-tiles of this CTA
+    const uint32_t stage_bytes = diag ? PANEL_BYTES : 2 * PANEL_BYTES;
+
+    auto issue = [&](int i) {
+        const int s = i % SST;
+        const int kt = blockIdx.y + i * gridDim.y;
+        uint8_t* st = base + (size_t)s * 2 * PANEL_BYTES;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_2d(st, &tmap, kt * SR, bi * SB, &full_bar[s]);
+        if (!diag) tma_load_2d(st + PANEL_BYTES, &tmap, kt * SR, bj * SB, &full_bar[s]);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < SST && i < nmy; ++i) issue(i);
+    }
+
+    // per-lane swizzled byte offsets of the 4 k-steps:  k = 2s + (t&1) + 8(t>>1);  chunk16 = (k>>1) ^ (col&7), col&7 == g
+    uint32_t koff[4];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+        const int k = 2 * s4 + (t & 1) + 8 * (t >> 1);
+        koff[s4] = (uint32_t)((((k >> 1) ^ g) << 4) | ((k & 1) << 3));
+    }
+    const uint32_t a_col = (uint32_t)(32 * wi + g) * 128u;
+    const uint32_t b_col = (uint32_t)(64 * wj + g) * 128u;
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    for (int i = 0; i < nmy; ++i) {
+        const int s = i % SST;
+        const uint32_t parity = (uint32_t)((i / SST) & 1);
+        mbar_wait(&full_bar[s], parity);
+        if (active) {
+            const uint8_t* pa = base + (size_t)s * 2 * PANEL_BYTES;
+            const uint8_t* pb = diag ? pa : pa + PANEL_BYTES;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                double a[4], b[8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+                    a[mi] = *reinterpret_cast<const double*>(pa + a_col + (uint32_t)mi * 1024u + koff[s4]);
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+                    b[ni] = *reinterpret_cast<const double*>(pb + b_col + (uint32_t)ni * 1024u + koff[s4]);
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+        }
+        __syncthreads();                               // every warp is done with stage s -> refill it
+        if (tid == 0 && i + SST < nmy) issue(i + SST);
+    }
+
+    double* P = partial + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (SB * SB);
+    if (active) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                const int il = 32 * wi + 8 * mi + g;
+                const int jl = 64 * wj + 8 * ni + 2 * t;
+                P[jl * SB + il] = acc[mi][ni][0];
+                P[(jl + 1) * SB + il] = acc[mi][ni][1];
+            }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+}  // namespace
+
+bool syrk_tma_eligible(const double* X, int64_t M, int64_t N, int64_t ld) {
+    if (N < 65 || N > kEigMaxN) return false;             // small n: the generic 64-block kernel is the better fit
+    if (M < 4096) return false;
+    if ((ld & 1) || (reinterpret_cast<uintptr_t>(X) & 15)) return false;   // TMA: 16-byte aligned base and stride
+    if (M >= (int64_t)1 << 31) return false;              // int32 TMA coordinates
+    return get_encode_fn() != nullptr;
+}
+
+SyrkPlan syrk_plan(int64_t M, int64_t N, int sm_count) {
+    SyrkPlan p;
+    p.nb = (int)((N + SB - 1) / SB);
+    p.nblk = p.nb * (p.nb + 1) / 2;
+    p.ntiles = (int)((M + SR - 1) / SR);
+    int ns = sm_count / p.nblk;
+    if (ns > p.ntiles) ns = p.ntiles;
+    if (ns < 1) ns = 1;
+    p.nsplit = ns;
+    p.partial_bytes = (size_t)p.nsplit * p.nblk * SB * SB * sizeof(double);
+    return p;
+}
+
+cudaError_t launch_syrk_tma(const double* X, int64_t M, int64_t N, int64_t ld, const SyrkPlan& plan, double* partial,
+                            double* G, cudaStream_t st, int64_t* launches) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)M, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)SR, (cuuint32_t)SB};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(X), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)SST * 2 * PANEL_BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(plan.nblk, plan.nsplit);
+    syrk_tma_kernel<<<grid, 256, smem, st>>>(map, partial, plan.nb, plan.ntiles);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = launch_gram_reduce(partial, plan.nsplit, plan.nblk, plan.nb, SB, (int)N, G, st);
+    if (launches) *launches += 2;
+    return e;
+}
+
+}  // namespace tlsq
