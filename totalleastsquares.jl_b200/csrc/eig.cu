@@ -104,7 +104,8 @@ template <int E>
 __global__ void __launch_bounds__(256)
 jacobi_cluster_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n, int spc,
                       double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
-                      int* __restrict__ info) {
+                      int* __restrict__ info, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;      // fast path succeeded: nothing to do (uniform over the cluster)
     constexpr int LEN = 32 * E;
     extern __shared__ double smem[];
     __shared__ int counters[64];
@@ -225,7 +226,8 @@ jacobi_cluster_kernel(const double* __restrict__ X0, const double* __restrict__ 
 template <int E>
 __global__ void __launch_bounds__(256)
 jacobi_global_kernel(int n, int np, double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
-                     int* __restrict__ info) {
+                     int* __restrict__ info, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -277,7 +279,9 @@ jacobi_global_kernel(int n, int np, double tol, int max_sweeps, double* __restri
 
 // prepare Xo/Vo for the global engine: Xo = X0 (or G), Vo = V0 (or I)
 __global__ void jacobi_global_init_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n,
-                                          double* __restrict__ Xo, double* __restrict__ Vo, int* __restrict__ info) {
+                                          double* __restrict__ Xo, double* __restrict__ Vo, int* __restrict__ info,
+                                          const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < 66) info[idx] = 0;
     if (idx >= (int64_t)n * n) return;
@@ -292,7 +296,9 @@ __global__ void jacobi_global_init_kernel(const double* __restrict__ X0, const d
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 eig_post_kernel(const double* __restrict__ Xo, const double* __restrict__ Vo, int n, int ncols,
-                double* __restrict__ lam_raw, double* __restrict__ lam_sorted, int* __restrict__ perm) {
+                double* __restrict__ lam_raw, double* __restrict__ lam_sorted, int* __restrict__ perm,
+                const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
     extern __shared__ double sl[];          // ncols lam + ncols valid flags (as double)
     double* lam = sl;
     double* valid = sl + ncols;
@@ -331,14 +337,17 @@ eig_post_kernel(const double* __restrict__ Xo, const double* __restrict__ Vo, in
 
 // Vs[:, r] = Vo[:, perm[r]]
 __global__ void permute_cols_kernel(const double* __restrict__ Vo, const int* __restrict__ perm, int n,
-                                    double* __restrict__ Vs) {
+                                    double* __restrict__ Vs, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
     const int r = blockIdx.x;
     const int j = perm[r];
     for (int i = threadIdx.x; i < n; i += blockDim.x) Vs[(int64_t)r * n + i] = Vo[(int64_t)j * n + i];
 }
 
 __global__ void svt_post_kernel(const double* __restrict__ lam, int n, double tau, int nukeA,
-                                double* __restrict__ sigma, double* __restrict__ fvec, int* __restrict__ svp) {
+                                double* __restrict__ sigma, double* __restrict__ fvec, int* __restrict__ svp,
+                                const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
@@ -359,7 +368,7 @@ __global__ void svt_post_kernel(const double* __restrict__ lam, int n, double ta
 
 template <int E>
 cudaError_t launch_cluster(const double* X0, const double* V0, int n, int C, int spc, double tol, int max_sweeps,
-                           double* Xo, double* Vo, int* info, cudaStream_t st) {
+                           double* Xo, double* Vo, int* info, const int* run_flag, cudaStream_t st) {
     constexpr int LEN = 32 * E;
     const size_t smem = (size_t)2 * 2 * spc * 2 * LEN * sizeof(double);
     auto kern = jacobi_cluster_kernel<E>;
@@ -381,17 +390,17 @@ cudaError_t launch_cluster(const double* X0, const double* V0, int n, int C, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, X0, V0, n, spc, tol, max_sweeps, Xo, Vo, info);
+    return cudaLaunchKernelEx(&cfg, kern, X0, V0, n, spc, tol, max_sweeps, Xo, Vo, info, run_flag);
 }
 
 template <int E>
 cudaError_t launch_global(int n, int np, double tol, int max_sweeps, double* Xo, double* Vo, int* info,
-                          int sm_count, cudaStream_t st) {
+                          const int* run_flag, int sm_count, cudaStream_t st) {
     int npairs = np / 2;
     int blocks = (npairs + 7) / 8;
     if (blocks > sm_count) blocks = sm_count;
     if (blocks < 1) blocks = 1;
-    void* args[] = {&n, &np, &tol, &max_sweeps, &Xo, &Vo, &info};
+    void* args[] = {&n, &np, &tol, &max_sweeps, &Xo, &Vo, &info, &run_flag};
     return cudaLaunchCooperativeKernel((void*)jacobi_global_kernel<E>, dim3(blocks), dim3(256), args, 0, st);
 }
 
@@ -404,7 +413,7 @@ size_t eig_work_doubles(int n) {
 }
 
 cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
-                        int sm_count, cudaStream_t st, int64_t* launches) {
+                        int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag) {
     cudaError_t e;
     const double tol = 1.0e-15 * (n < 16 ? 4.0 : sqrt((double)n));   // relative orthogonality threshold
     const int max_sweeps = 30;
@@ -424,32 +433,32 @@ cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, dou
         while (C < 16 && (mneed + C - 1) / C > 8) C *= 2;
         const int spc = (mneed + C - 1) / C;
         ncols = 2 * C * spc;
-        if (n <= 32) e = launch_cluster<1>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
-        else if (n <= 64) e = launch_cluster<2>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
-        else if (n <= 128) e = launch_cluster<4>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
-        else e = launch_cluster<8>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, st);
+        if (n <= 32) e = launch_cluster<1>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, run_flag, st);
+        else if (n <= 64) e = launch_cluster<2>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, run_flag, st);
+        else if (n <= 128) e = launch_cluster<4>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, run_flag, st);
+        else e = launch_cluster<8>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, run_flag, st);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 1;
     } else {
         const int np = (n + 1) & ~1;
         ncols = n;
         jacobi_global_init_kernel<<<(unsigned)(((int64_t)n * n + 255) / 256), 256, 0, st>>>(X0, V0, n, w.Xo, w.Vo,
-                                                                                           w.info);
+                                                                                           w.info, run_flag);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        e = launch_global<16>(n, np, tol, max_sweeps, w.Xo, w.Vo, w.info, sm_count, st);
+        e = launch_global<16>(n, np, tol, max_sweeps, w.Xo, w.Vo, w.info, run_flag, sm_count, st);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 2;
     }
-    eig_post_kernel<<<1, 256, 2 * ncols * sizeof(double), st>>>(w.Xo, w.Vo, n, ncols, w.lam_raw, lam, w.perm);
+    eig_post_kernel<<<1, 256, 2 * ncols * sizeof(double), st>>>(w.Xo, w.Vo, n, ncols, w.lam_raw, lam, w.perm, run_flag);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    permute_cols_kernel<<<n, 128, 0, st>>>(w.Vo, w.perm, n, Vs);
+    permute_cols_kernel<<<n, 128, 0, st>>>(w.Vo, w.perm, n, Vs, run_flag);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
 
 cudaError_t launch_svt_post(const double* lam, int n, double tau, int nukeA, double* sigma, double* fvec,
-                            int* svp, cudaStream_t st, int64_t* launches) {
-    svt_post_kernel<<<1, 256, 0, st>>>(lam, n, tau, nukeA, sigma, fvec, svp);
+                            int* svp, cudaStream_t st, int64_t* launches, const int* run_flag) {
+    svt_post_kernel<<<1, 256, 0, st>>>(lam, n, tau, nukeA, sigma, fvec, svp, run_flag);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

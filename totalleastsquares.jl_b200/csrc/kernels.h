@@ -63,12 +63,35 @@ size_t eig_work_doubles(int n);
 // Eigen-decomposition of symmetric PSD G (n x n, ld n).  If V0 != nullptr it must hold an orthogonal n x n
 // warm-start basis (previous eigenvectors).  Outputs: lam (n, descending), Vs (n x n sorted eigenvector columns).
 // Vs may alias V0.
+// run_flag (optional, device): the whole decomposition is skipped on the device when run_flag[1] == 0.
 cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
-                        int sm_count, cudaStream_t st, int64_t* launches);
+                        int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag = nullptr);
+
+// Fast path (eig_fast.cu, 64 < n <= 256): warm-started block subspace iteration for the dominant eigenpairs +
+// a rigorous certificate of the count #{sigma >= tau}.  flags[1] != 0 afterwards means "fall back to launch_eigh".
+struct EigFastWork {
+    double* Qb;      // n x 32 warm-start basis carried between ALM iterations
+    double* Qwork;   // n x 32 working basis of the subspace iteration
+    double* Qout;    // n x 32 sorted Ritz vectors
+    double* X;       // n x 32 G * Qwork
+    double* theta;   // 32 Ritz values (descending)
+    double* Ca;      // n x n certificate ping
+    double* Cb;      // n x n certificate pong
+    double* f2;      // 16 squared Frobenius norms of the squaring chain
+    int* flags;      // [0] converged [1] need_full [2] svp [3] SI steps [4] certified [5] sweeps of the last SI step
+};
+size_t eig_fast_work_doubles(int n);
+bool eig_fast_supported(int n);
+EigFastWork eig_fast_carve(double* base, int n);
+cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
+                            double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches);
+// Qb = Vs[:, 0:32] (skipped on the device when flags != null and flags[1] == 0)
+cudaError_t launch_copy_block(const double* Vs, int n, double* Qb, const int* flags, cudaStream_t st,
+                              int64_t* launches);
 
 // sigma[i] = sqrt(max(lam[i],0)); svp = #{sigma >= tau}; fvec[i] = nuke ? (sigma-tau)/sigma : 1  (0 beyond svp)
 cudaError_t launch_svt_post(const double* lam, int n, double tau, int nukeA, double* sigma, double* fvec,
-                            int* svp, cudaStream_t st, int64_t* launches);
+                            int* svp, cudaStream_t st, int64_t* launches, const int* run_flag = nullptr);
 
 // ----------------------------------------------------------------------------------------------------
 // Fused ALM epilogue: one pass over a row tile does  E-step, W, T = W V_r, A = clamp(T diag(f) V_r'),

@@ -259,6 +259,17 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         ew.info = reinterpret_cast<int*>(base);
     }
     double* hp = h->h_pin;
+    // fast eigen path state (dominant-subspace iteration, see eig_fast.cu)
+    static const bool no_fast = getenv("TLSQ_NO_FAST_EIG") != nullptr;
+    const bool fast_ok = eig_fast_supported(n) && !no_fast;
+    DevBuf bFast;
+    EigFastWork fw = {};
+    if (fast_ok) {
+        CK(bFast.alloc(eig_fast_work_doubles(n) * 8, st));
+        fw = eig_fast_carve(bFast.as<double>(), n);
+    }
+    bool have_q = false;
+    bool last_was_fast = false;
 
     // ---- setup (:174-185) --------------------------------------------------------------------------------
     CK(cudaMemsetAsync(dscal, 0, 16 * 8, st));
@@ -323,8 +334,20 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
         {
             Phase ph(h, TLSQ_PHASE_EIG);
-            CK(launch_eigh(G, n, Vs, ew, lam, Vs, sms, st, L));                          // warm start from V_{k-1}
-            CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L));            // :198
+            if (fast_ok && have_q) {
+                // dominant eigenpairs + certified count; the full Jacobi below only runs (device-side flag) when the
+                // fast path could not prove the count
+                CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L));
+                CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
+                CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L, fw.flags));   // :198
+                CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
+                last_was_fast = true;
+            } else {
+                CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
+                CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L));        // :198
+                if (fast_ok) { CK(launch_copy_block(Vs, n, fw.Qb, nullptr, st, L)); have_q = true; }
+                last_was_fast = false;
+            }
         }
         // fused epilogue  (:188-192, 205-222)
         CK(cudaMemsetAsync(dscal, 0, 8, st));
@@ -343,12 +366,17 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
         static const bool dbg_eig = getenv("TLSQ_DEBUG_EIG") != nullptr;
-        if (dbg_eig) CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
+        if (dbg_eig) {
+            CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
+            if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
         if (dbg_eig) {
-            int sw;
+            int sw, fl[8] = {0};
             memcpy(&sw, hp + 2, 4);
-            fprintf(stderr, "[tlsq] iter %lld: jacobi sweeps %d\n", (long long)k, sw);
+            if (fast_ok) memcpy(fl, hp + 4, 32);
+            fprintf(stderr, "[tlsq] iter %lld: full-jacobi sweeps %d | fast: conv %d need_full %d svp %d si_steps %d "
+                            "certified %d si_sweeps %d\n", (long long)k, sw, fl[0], fl[1], fl[2], fl[3], fl[4], fl[5]);
         }
         const double zz = hp[0];
         int svp;
@@ -390,6 +418,11 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
 
     // ---- outputs (:238) ----------------------------------------------------------------------------------
     Phase ph_final(h, TLSQ_PHASE_FINALIZE);
+    if (fast_ok && last_was_fast && (o.S || o.Vt || o.U)) {
+        // the fast path only carries the dominant block; the returned SVD (:238) needs the full spectrum of the last W
+        CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
+        CK(launch_svt_post(lam, n, im_last, nukeA, sigma, fvec, dsvp, st, L));
+    }
     // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
     // produced before A_k is copied there.
     if (o.E)
