@@ -60,6 +60,47 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Plane rotation that (nearly) annihilates gamma = x_p . x_q given alpha = |x_p|^2, beta = |x_q|^2.
+// The tangent only needs ~20 bits (a slightly inexact angle still converges; later sweeps finish the job), so it is
+// built from the single-instruction MUFU reciprocal / rsqrt approximations instead of four IEEE FP64 div/sqrt
+// sequences (measured: those dominated the latency of a Jacobi round).  c is Newton-refined to full precision so
+// that c^2 + s^2 == 1 to rounding and the accumulated V stays orthogonal.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_approx(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double rsqrt_approx(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+// returns false when the pair is already orthogonal to the relative tolerance `tol` (or a column is null)
+__device__ __forceinline__ bool jacobi_cs(double alpha, double beta, double gamma, double tol, double& c, double& s) {
+    const double lim2 = tol * tol * alpha * beta;
+    if (!(gamma * gamma > lim2) || lim2 == 0.0) return false;
+    const double zeta = (beta - alpha) * (0.5 * rcp_approx(gamma));
+    const double az = fabs(zeta);
+    double tt;
+    if (az > 1.0e7) {
+        tt = 0.5 * rcp_approx(az);                                   // 1/(|z| + sqrt(1+z^2)) -> 1/(2|z|)
+    } else {
+        const double q = fma(zeta, zeta, 1.0);
+        const double root = q * rsqrt_approx(q);                     // ~sqrt(1 + zeta^2)
+        tt = rcp_approx(az + root);
+    }
+    tt = copysign(tt, zeta);
+    const double q2 = fma(tt, tt, 1.0);                              // in [1, 2]
+    double r = rsqrt_approx(q2);
+    r = r * fma(-0.5 * q2 * r, r, 1.5);                              // two Newton steps: r -> 1/sqrt(q2) to FP64
+    r = r * fma(-0.5 * q2 * r, r, 1.5);
+    c = r;
+    s = r * tt;
+    return true;
+}
+
 // Matrix source: either a dense column-major matrix or an implicit Hankel embedding of a signal
 // (H[k,l] = y[k*lag + l], src/robustPCA.jl:76-92, never materialised).
 struct MatSrc {

@@ -76,12 +76,8 @@ __device__ __forceinline__ bool jacobi_rotate(double (&xp)[E], double (&xq)[E], 
     alpha = warp_sum(alpha);
     beta = warp_sum(beta);
     gamma = warp_sum(gamma);
-    const double lim = tol * sqrt(alpha) * sqrt(beta);
-    if (!(fabs(gamma) > lim) || lim == 0.0) return false;      // already orthogonal (or a null column)
-    const double zeta = (beta - alpha) / (2.0 * gamma);
-    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-    const double c = 1.0 / sqrt(fma(tt, tt, 1.0));
-    const double s = c * tt;
+    double c, s;
+    if (!jacobi_cs(alpha, beta, gamma, tol, c, s)) return false;       // already orthogonal (or a null column)
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const double a = xp[e], b = xq[e];

@@ -116,12 +116,8 @@ __device__ __forceinline__ bool rotate_pair(double (&xp)[E], double (&xq)[E], do
     alpha = warp_sum(alpha);
     beta = warp_sum(beta);
     gamma = warp_sum(gamma);
-    const double lim = tol * sqrt(alpha) * sqrt(beta);
-    if (!(fabs(gamma) > lim) || lim == 0.0) return false;
-    const double zeta = (beta - alpha) / (2.0 * gamma);
-    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-    const double c = 1.0 / sqrt(fma(tt, tt, 1.0));
-    const double s = c * tt;
+    double c, s;
+    if (!jacobi_cs(alpha, beta, gamma, tol, c, s)) return false;       // already orthogonal (or a null column)
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const double a = xp[e], b = xq[e];
@@ -334,6 +330,31 @@ __global__ void copy_block_kernel(const double* __restrict__ Vs, int n, double* 
         Qb[idx] = Vs[idx];
 }
 
+// ||G||_F^2 of an n x n matrix
+__global__ void __launch_bounds__(256)
+fro2_kernel(const double* __restrict__ G, int64_t nn, double* __restrict__ out) {
+    double f2 = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nn; idx += (int64_t)gridDim.x * blockDim.x)
+        f2 = fma(G[idx], G[idx], f2);
+    f2 = warp_sum(f2);
+    if ((threadIdx.x & 31) == 0 && f2 != 0.0) atomicAdd(out, f2);
+}
+
+// bounds[0] <= lambda_max(G) <= bounds[1] from the Frobenius norms of the squaring chain:
+//   upper: u_k = 1,          u_j = sqrt(f_{j+1} u_{j+1});   lower: l_k = 1/sqrt(n), l_j = sqrt(f_{j+1} l_{j+1})
+__global__ void lmax_bounds_kernel(const double* __restrict__ f2, int nsq, int n, double* __restrict__ bounds) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double u = 1.0, l = 1.0 / sqrt((double)n);
+    for (int j = nsq - 1; j >= 0; --j) {
+        const double f = sqrt(f2[j + 1]);
+        u = sqrt(f * u);
+        l = sqrt(f * l);
+    }
+    const double f0 = sqrt(f2[0]);
+    bounds[0] = f0 * l;
+    bounds[1] = f0 * u;
+}
+
 template <int E>
 cudaError_t launch_si(const double* X, double* Q, int n, double tau2, double tol_jac, double tol_res, int last,
                       double* theta, double* Qout, int* flags, cudaStream_t st) {
@@ -368,6 +389,27 @@ EigFastWork eig_fast_carve(double* base, int n) {
     return w;
 }
 
+cudaError_t launch_lmax_bounds(const double* G, int n, double* Ca, double* Cb, double* f2, double* bounds,
+                               cudaStream_t st, int64_t* launches) {
+    constexpr int NSQ = 10;      // bracket ratio n^(1/2^(NSQ+1)): 0.27 % at n = 256
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(f2, 0, 16 * sizeof(double), st)) != cudaSuccess) return e;
+    fro2_kernel<<<32, 256, 0, st>>>(G, (int64_t)n * n, f2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const dim3 gs((n + AT - 1) / AT, (n + AT - 1) / AT);
+    const double* cin = G;
+    double* cout = Ca;
+    for (int j = 0; j < NSQ; ++j) {
+        atb_kernel<<<gs, 256, 0, st>>>(cin, n, cin, n, n, n, n, f2 + j, cout, n, 1, f2 + j + 1, nullptr, 0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        cin = cout;
+        cout = (cout == Ca) ? Cb : Ca;
+    }
+    lmax_bounds_kernel<<<1, 32, 0, st>>>(f2, NSQ, n, bounds);
+    if (launches) *launches += NSQ + 2;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_copy_block(const double* Vs, int n, double* Qb, const int* flags, cudaStream_t st,
                               int64_t* launches) {
     copy_block_kernel<<<8, 256, 0, st>>>(Vs, n, Qb, flags);
@@ -377,7 +419,7 @@ cudaError_t launch_copy_block(const double* Vs, int n, double* Qb, const int* fl
 
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches) {
-    constexpr int NSI = 6;       // subspace-iteration steps attempted before falling back
+    constexpr int NSI = 12;      // subspace-iteration steps attempted before falling back (skipped launches exit at once)
     constexpr int NSQ = 6;       // squarings of the certificate: bound within n^(1/128) of lambda_max
     cudaError_t e;
     const double tau2 = tau * tau;

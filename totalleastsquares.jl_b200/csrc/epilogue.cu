@@ -162,6 +162,7 @@ epilogue_kernel(const EpiArgs a, int ntiles) {
                 a.An[off] = an;
                 a.Yn[off] = yn;
                 if (a.Eout) a.Eout[off] = e;
+                if (a.Zout) a.Zout[off] = z;
                 if (a.Wn) {                                                           // SVT input of iteration k+1
                     double e2, w2;
                     alm_ew(d, an, yn, a.im_next, a.eps_next, a.nonnegE, e2, w2);

@@ -85,6 +85,10 @@ bool eig_fast_supported(int n);
 EigFastWork eig_fast_carve(double* base, int n);
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches);
+// bounds[0] <= lambda_max(G) <= bounds[1] (device doubles) for a symmetric PSD n x n G by 10 normalised squarings
+// (bracket ratio n^(1/2048)).  Ca, Cb: n x n scratch, f2: 16 doubles scratch.
+cudaError_t launch_lmax_bounds(const double* G, int n, double* Ca, double* Cb, double* f2, double* bounds,
+                               cudaStream_t st, int64_t* launches);
 // Qb = Vs[:, 0:32] (skipped on the device when flags != null and flags[1] == 0)
 cudaError_t launch_copy_block(const double* Vs, int n, double* Qb, const int* flags, cudaStream_t st,
                               int64_t* launches);
@@ -104,6 +108,7 @@ struct EpiArgs {
     double* An;         // A_k      (may alias Ap: the pass is tile-local)
     double* Yn;         // Y_k      (may alias Yp)
     double* Eout;       // optional E_k
+    double* Zout;       // optional Z_k = D - A_k - E_k (materialised for the exact stop test)
     double* Wn;         // optional W_{k+1} = D - E_{k+1} + Y_k/mu_{k+1} (materialised SVT input of the next iteration)
     double im_next, eps_next;   // 1/mu_{k+1}, lambda/mu_{k+1}
     double* Uout;       // MODE U only: M x d
@@ -117,6 +122,12 @@ struct EpiArgs {
 };
 cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_count, cudaStream_t st,
                             int64_t* launches);
+
+// Streaming form of the epilogue (stream.cu) for a materialised W and svp <= kStreamMaxRank (svp known on the host):
+// T (M x 32 workspace) = W V_r diag(f), then one coalesced element-wise pass.  Needs a.Wn != nullptr.
+constexpr int kStreamMaxRank = 32;
+cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, double* T, int svp, bool hankel, int sm_count,
+                                   cudaStream_t st, int64_t* launches);
 
 // element-wise helpers ------------------------------------------------------------------------------
 // maxabs: *out = max |D_ij| (out must be zeroed);  init: Y = D / dual, A = 0

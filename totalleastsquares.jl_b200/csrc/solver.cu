@@ -224,9 +224,10 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     SyrkPlan splan = syrk_plan(M, N, sms);
     const size_t part_bytes = use_w && splan.partial_bytes > plan.partial_bytes ? splan.partial_bytes
                                                                                  : plan.partial_bytes;
-    DevBuf bW;
-    if (use_w) CK(bW.alloc(mn * 8, st));
+    DevBuf bW, bT;
+    if (use_w) { CK(bW.alloc(mn * 8, st)); CK(bT.alloc((size_t)M * kStreamMaxRank * 8, st)); }
     double* Wbuf = use_w ? bW.as<double>() : nullptr;
+    double* Tbuf = use_w ? bT.as<double>() : nullptr;
 
     DevBuf bA0, bA1, bY0, bY1, bPart, bG, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
     // A ping-pong: reuse the caller's A buffer as one side when given
@@ -270,6 +271,15 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     }
     bool have_q = false;
     bool last_was_fast = false;
+    // exact stop test: Z is materialised by the epilogue when the Frobenius bracket is expected to be undecided, its
+    // Gram runs on the TMA SYRK kernel and lambda_max is bracketed by repeated squaring
+    DevBuf bZ, bSq;
+    double* Zbuf = nullptr;
+    CK(bSq.alloc(((size_t)2 * n * n + 32) * 8, st));
+    double* sqA = bSq.as<double>();
+    double* sqB = sqA + (size_t)n * n;
+    double* sqf = sqB + (size_t)n * n;         // 16 f2 + 2 bounds
+    double prev_fro = 1.0e300;
 
     // ---- setup (:174-185) --------------------------------------------------------------------------------
     CK(cudaMemsetAsync(dscal, 0, 16 * 8, st));
@@ -356,11 +366,25 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
         ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
         ea.zz = dscal;
+        // will the Frobenius bracket [fro/sqrt(d), fro] probably straddle tol?  (fro shrinks by < 8x per iteration)
+        const bool want_z = use_w && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
+        if (want_z && !Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
+        ea.Zout = want_z ? Zbuf : nullptr;
         const double mu_next = fmin(mu * p.rho, mubar);                                  // :223
         ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
+        int svp = 0;
+        if (use_w) {
+            // the streaming epilogue is specialised on the rank: fetch svp now (one short extra host sync)
+            CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            memcpy(&svp, hp + 1, 4);
+        }
         {
             Phase ph(h, TLSQ_PHASE_EPILOGUE);
-            CK(launch_epilogue(ea, hankel, false, sms, st, L));
+            if (use_w && svp <= kStreamMaxRank)
+                CK(launch_stream_epilogue(ea, Wbuf, Tbuf, svp, hankel, sms, st, L));
+            else
+                CK(launch_epilogue(ea, hankel, false, sms, st, L));
         }
         CKR(allreduce(h, dscal, 1, kNcclSum));
         CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
@@ -379,7 +403,6 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                             "certified %d si_sweeps %d\n", (long long)k, sw, fl[0], fl[1], fl[2], fl[3], fl[4], fl[5]);
         }
         const double zz = hp[0];
-        int svp;
         memcpy(&svp, hp + 1, 4);
         svp_last = svp;
         im_last = im; eps_last = eps; prev_idx = cur; last_idx = nxt;
@@ -394,17 +417,33 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             else if (fro / sqrt(dmin) >= p.tol) converged = false;
             else need_exact = true;
         }
+        prev_fro = fro;
         if (need_exact) {
             Phase ph(h, TLSQ_PHASE_EXACT_COST);
-            gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;
-            CK(launch_gram(gs, GRAM_Z, hankel, plan, bPart.as<double>(), G2, st, L));
+            if (want_z) {
+                CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
+            } else {
+                gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;
+                CK(launch_gram(gs, GRAM_Z, hankel, plan, bPart.as<double>(), G2, st, L));
+            }
             CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
-            CK(launch_eigh(G2, n, nullptr, ew, lam2, Vs2, sms, st, L));
-            CK(cudaMemcpyAsync(hp, lam2, 8, cudaMemcpyDeviceToHost, st));
+            // bracket lambda_max(Z'Z) by repeated squaring; only a bracket that straddles tol^2 needs the Jacobi
+            CK(launch_lmax_bounds(G2, n, sqA, sqB, sqf, sqf + 16, st, L));
+            CK(cudaMemcpyAsync(hp, sqf + 16, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            const double cost = sqrt(hp[0] > 0.0 ? hp[0] : 0.0) / d_norm;
-            cost_rec = cost;
-            converged = cost < p.tol;
+            const double c_lo = sqrt(hp[0] > 0.0 ? hp[0] : 0.0) / d_norm;
+            const double c_hi = sqrt(hp[1] > 0.0 ? hp[1] : 0.0) / d_norm;
+            const bool bracket_ok = (hp[0] == hp[0]) && (hp[1] == hp[1]);
+            if (!exact_cost && bracket_ok && c_hi < p.tol) { converged = true; cost_rec = -c_hi; }
+            else if (!exact_cost && bracket_ok && c_lo >= p.tol) { converged = false; cost_rec = -c_hi; }
+            else {
+                CK(launch_eigh(G2, n, nullptr, ew, lam2, Vs2, sms, st, L));
+                CK(cudaMemcpyAsync(hp, lam2, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                const double cost = sqrt(hp[0] > 0.0 ? hp[0] : 0.0) / d_norm;
+                cost_rec = cost;
+                converged = cost < p.tol;
+            }
         }
         if (o.hist) {
             o.hist[3 * (k - 1) + 0] = (double)k;
@@ -440,7 +479,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
         EpiArgs ea;
         ea.D = D; ea.Ap = Abuf[prev_idx]; ea.Yp = Ybuf[prev_idx]; ea.An = nullptr; ea.Yn = nullptr;
-        ea.Wn = nullptr; ea.im_next = 0.0; ea.eps_next = 0.0;
+        ea.Wn = nullptr; ea.im_next = 0.0; ea.eps_next = 0.0; ea.Zout = nullptr;
         ea.Eout = nullptr; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
         ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last; ea.mu = 0.0; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
         ea.zz = dscal;
