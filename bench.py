@@ -168,7 +168,7 @@ def run_reference(args, w, rank):
             "config": {"workload": w["name"]},
             "cpu_baseline": {"value": value, "unit": unit, "cores": cpu_cores(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    EMIT(json.dumps(line))
 
 
 def metric_name(w):
@@ -357,12 +357,30 @@ def run_b200(args, w, rank, world, local_rank):
             sample = f"rpca_ga(X,2) of the oracle port on the first 100000 rows ({dt:.1f} s), scaled by 100000/{M}"
             unit = "GA iterations/s"
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cpu_cores(), "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    EMIT(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Route fd 1 to stderr while the benchmark runs (NCCL prints its version banner on stdout when NCCL_DEBUG is set)
+    and hand back a writer for the one JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text: str):
+        sys.stdout.flush()
+        os.write(real, (text + "\n").encode())
+    return emit
+
+
+EMIT = None
+
+
 def main():
+    global EMIT
+    EMIT = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

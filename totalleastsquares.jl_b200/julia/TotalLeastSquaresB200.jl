@@ -1,0 +1,163 @@
+# TotalLeastSquaresB200.jl -- Julia shim over libtlsq_b200.so (include/tlsq_b200.h).
+#
+# Drop-in replacements for the robust-PCA hot path of TotalLeastSquares.jl with the reference's own signatures,
+# defaults and return types:
+#     rpca(D; λ, maxrank, iters, tol, ρ, verbose, nonnegA, nonnegE, hankel, nukeA, svd, opnorm, kwargs...)
+#                                   -> (A, E, s::LinearAlgebra.SVD, sv::Int)        src/robustPCA.jl:156-239
+#     rpca_ga(X, r, U; verbose, tol, iters, μ) -> Q                                 src/robustPCA.jl:255-306
+#     lowrankfilter(y, n; sv, lag, tol, svd, kwargs...) -> yf                       src/robustPCA.jl:119-128
+# Everything numerical happens behind `ccall`; this file only marshals arguments.  Julia is NOT available in the
+# build image of this repository, so this shim could not be executed there: it is kept deliberately thin and the
+# same C entry points are exercised by the Python mirror (totalleastsquares.jl_b200/__init__.py) in the test-suite.
+#
+# Usage inside TotalLeastSquares.jl (see INTEGRATION.md):
+#     include("TotalLeastSquaresB200.jl"); using .TotalLeastSquaresB200
+#     A, E, s, sv = TotalLeastSquaresB200.rpca(D; nonnegA = true)
+module TotalLeastSquaresB200
+
+using LinearAlgebra
+
+export rpca, rpca_ga, lowrankfilter
+
+const LIB = get(ENV, "TLSQ_B200_LIB", joinpath(@__DIR__, "..", "libtlsq_b200.so"))
+
+const TLSQ_NONNEG_A   = UInt32(1) << 0
+const TLSQ_NONNEG_E   = UInt32(1) << 1
+const TLSQ_HANKEL     = UInt32(1) << 2
+const TLSQ_NO_NUKE_A  = UInt32(1) << 3
+const TLSQ_EXACT_COST = UInt32(1) << 4
+
+const HANDLE = Ref{Ptr{Cvoid}}(C_NULL)
+
+function check(code::Cint)
+    code == 0 && return
+    msg = unsafe_string(ccall((:tlsq_last_error, LIB), Cstring, ()))
+    # TLSQ_ERR_ARG (1) mirrors the reference's @assert / ArgumentError behaviour; everything else is a runtime error.
+    code == 1 ? throw(ArgumentError(msg)) : error("tlsq_b200 error $code: $msg")
+end
+
+function handle()
+    if HANDLE[] == C_NULL
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:tlsq_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), 0, h))   # no GPU => error, no CPU fallback
+        HANDLE[] = h[]
+    end
+    HANDLE[]
+end
+
+_only_f64(x, name) = eltype(x) === Float64 ||
+    throw(ArgumentError("$name: only Float64 is accelerated by TotalLeastSquaresB200 (got $(eltype(x))); no CPU fallback"))
+
+"""
+    A, E, s, sv = rpca(D; λ, maxrank, iters, tol, ρ, verbose, nonnegA, nonnegE, hankel, nukeA)
+
+Same keyword list and defaults as `TotalLeastSquares.rpca` (src/robustPCA.jl:156-170); unknown keywords are swallowed
+like the reference does (`kwargs...`, :170).  Non-default `svd` / `opnorm` callables cannot cross the C ABI.
+"""
+function rpca(D::AbstractMatrix{T};
+              λ              = real(T)(1.0 / sqrt(maximum(size(D)))),
+              maxrank        = typemax(Int),
+              iters::Int     = 1000,
+              tol            = sqrt(eps(real(T))),
+              ρ              = real(T)(1.5),
+              verbose::Bool  = false,
+              nonnegA::Bool  = false,
+              nonnegE::Bool  = false,
+              hankel::Bool   = false,
+              nukeA          = true,
+              svd::F1        = LinearAlgebra.svd!,
+              opnorm::F2     = LinearAlgebra.opnorm,
+              kwargs...) where {F1 <: Function, F2 <: Function, T}
+    _only_f64(D, "rpca")
+    (svd ∈ (LinearAlgebra.svd, LinearAlgebra.svd!) && opnorm === LinearAlgebra.opnorm) ||
+        throw(ArgumentError("rpca: custom svd/opnorm callables are not supported by the B200 path (no CPU fallback)"))
+    Dd = Matrix{Float64}(D)                         # dense, column-major (the reference copies too, :176)
+    M, N = size(Dd)
+    d = min(M, N)
+    A, E = Matrix{Float64}(undef, M, N), Matrix{Float64}(undef, M, N)
+    U, S, Vt = Matrix{Float64}(undef, M, d), Vector{Float64}(undef, d), Matrix{Float64}(undef, d, N)
+    sv, its, conv = Ref{Int64}(0), Ref{Int64}(0), Ref{Int32}(0)
+    hist = Matrix{Float64}(undef, 3, max(iters, 1))                  # column k = (k, svp, cost)
+    flags = (nonnegA ? TLSQ_NONNEG_A : UInt32(0)) | (nonnegE ? TLSQ_NONNEG_E : UInt32(0)) |
+            (hankel ? TLSQ_HANKEL : UInt32(0)) | (nukeA ? UInt32(0) : TLSQ_NO_NUKE_A) |
+            (verbose ? TLSQ_EXACT_COST : UInt32(0))
+    mr = maxrank == typemax(Int) ? Int64(0) : Int64(maxrank)
+    GC.@preserve Dd A E U S Vt hist begin
+        check(ccall((:tlsq_rpca_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Float64, Int64, Int64, Float64, Float64, UInt32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
+                    handle(), Dd, M, N, Float64(λ), mr, Int64(iters), Float64(tol), Float64(ρ), flags,
+                    A, E, U, S, Vt, sv, its, conv, hist))
+    end
+    if verbose                                                        # :226, :229
+        for k in 1:its[]
+            println("$(k) cost: $(round(abs(hist[3, k]), sigdigits = 4))")
+        end
+        conv[] != 0 && println("converged")
+    end
+    conv[] == 0 && @warn "Maximum number of iterations reached, cost: $(abs(hist[3, max(its[], 1)])), tol: $tol"   # :232
+    A, E, LinearAlgebra.SVD(U, S, Vt), Int(sv[])
+end
+
+"""
+    Q = rpca_ga(X, r = minimum(size(X)), U = similar(X); verbose = false, tol = 1e-7, iters = 1000)
+
+The start vector of every component is drawn here with `randn(d)` so the global RNG is consumed exactly like the
+reference does (src/robustPCA.jl:286).  `U` is accepted for signature compatibility (the normalised copy is never
+formed on the GPU).  Custom averages `μ` are not supported by the accelerated path.
+"""
+function rpca_ga(X::AbstractMatrix{T}, r = minimum(size(X)), U = nothing; verbose = false, tol = 1e-7,
+                 iters::Int = 1000, μ = nothing, kwargs...) where T
+    _only_f64(X, "rpca_ga")
+    μ === nothing || throw(ArgumentError("rpca_ga: custom averages are not supported by the B200 path"))
+    Xd = Matrix{Float64}(X)
+    d, N = size(Xd)
+    q0 = Matrix{Float64}(undef, d, r)
+    for i in 1:r
+        q0[:, i] .= randn(d)                                          # :286, one draw per component, in order
+    end
+    Q = Matrix{Float64}(undef, d, r)
+    its = Vector{Int64}(undef, r)
+    GC.@preserve Xd q0 Q its begin
+        check(ccall((:tlsq_rpca_ga_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Float64, Int64, Ptr{Float64}, Ptr{Int64}),
+                    handle(), Xd, d, N, Int64(r), q0, Float64(tol), Int64(iters), Q, its))
+    end
+    verbose && foreach(i -> @info("Component $i converged after $(its[i]) iterations"), 1:r)
+    any(>=(iters), its) && @warn "Reached maximum number of iterations"   # :303
+    Q
+end
+
+"""
+    yf = lowrankfilter(y, n = min(length(y) ÷ 20, 2000); lag = 1, tol = 1e-3, kwargs...)
+
+Single-channel signals with `sv = 0` run on the GPU with an implicit (never materialised) Hankel embedding.
+"""
+function lowrankfilter(y::AbstractVector{T}, n = min(size(y, 1) ÷ 20, 2000); sv = 0, lag = 1, tol = 1e-3,
+                       svd = LinearAlgebra.svd!, λ = nothing, maxrank = typemax(Int), iters::Int = 1000, ρ = 1.5,
+                       verbose::Bool = false, nonnegA::Bool = false, nonnegE::Bool = false, hankel::Bool = false,
+                       nukeA = true, kwargs...) where T
+    _only_f64(y, "lowrankfilter")
+    sv <= 0 || throw(ArgumentError("lowrankfilter: the sv > 0 SSA branch is not part of the B200 path"))
+    N = length(y)
+    n <= N / 2 || throw(AssertionError("L has to be less than N/2 = $(N/2)"))       # :79
+    lag <= n || throw(AssertionError("lag must be <= L"))                            # :80
+    yd = Vector{Float64}(y)
+    yf = Vector{Float64}(undef, N)
+    svo, its, conv = Ref{Int64}(0), Ref{Int64}(0), Ref{Int32}(0)
+    flags = (nonnegA ? TLSQ_NONNEG_A : UInt32(0)) | (nonnegE ? TLSQ_NONNEG_E : UInt32(0)) |
+            (hankel ? TLSQ_HANKEL : UInt32(0)) | (nukeA ? UInt32(0) : TLSQ_NO_NUKE_A)
+    mr = maxrank == typemax(Int) ? Int64(0) : Int64(maxrank)
+    GC.@preserve yd yf begin
+        check(ccall((:tlsq_lowrankfilter_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Int64, Int64, Float64, Float64, UInt32,
+                     Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
+                    handle(), yd, N, Int64(n), Int64(lag), λ === nothing ? 0.0 : Float64(λ), mr, Int64(iters),
+                    Float64(tol), Float64(ρ), flags, yf, svo, its, conv, C_NULL))
+    end
+    conv[] == 0 && @warn "Maximum number of iterations reached, tol: $tol"
+    yf
+end
+
+end # module
