@@ -105,7 +105,7 @@ constexpr int SIB = 32;          // block width
 
 template <int E>
 __device__ __forceinline__ bool rotate_pair(double (&xp)[E], double (&xq)[E], double (&vp)[E], double (&vq)[E],
-                                            double tol) {
+                                            double tol, double wanted2) {
     double alpha = 0.0, beta = 0.0, gamma = 0.0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -117,7 +117,8 @@ __device__ __forceinline__ bool rotate_pair(double (&xp)[E], double (&xq)[E], do
     beta = warp_sum(beta);
     gamma = warp_sum(gamma);
     double c, s;
-    if (!jacobi_cs(alpha, beta, gamma, tol, c, s)) return false;       // already orthogonal (or a null column)
+    const double tl = (alpha < wanted2 && beta < wanted2) ? 1.0e-6 : tol;
+    if (!jacobi_cs(alpha, beta, gamma, tl, c, s)) return false;        // already orthogonal (or a null column)
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const double a = xp[e], b = xq[e];
@@ -131,19 +132,19 @@ __device__ __forceinline__ bool rotate_pair(double (&xp)[E], double (&xq)[E], do
 }
 
 // flags: [0] conv, [1] need_full, [2] svp, [3] SI steps used, [4] certified, [5] jacobi sweeps of the last SI step
-template <int E>
-__global__ void __launch_bounds__(512, 1)
-si_jacobi_kernel(const double* __restrict__ X, double* __restrict__ Q, int n, double tau2, double tol_jac,
-                 double tol_res, int last_step, double* __restrict__ theta_out, double* __restrict__ Qout,
-                 int* __restrict__ flags) {
+template <int E, int BW>
+__global__ void __launch_bounds__(16 * BW, 1)
+si_jacobi_kernel(const double* __restrict__ X, double* __restrict__ Q, int n, double tau2, int min_wanted,
+                 double tol_jac, double tol_res, int last_step, double* __restrict__ theta_out,
+                 double* __restrict__ Qout, int* __restrict__ flags) {
     if (flags[0] == 1 || flags[1] == 1) return;
     constexpr int LEN = 32 * E;
     extern __shared__ double sm[];                 // SIB slots x [X part | Q part]
-    __shared__ double th[SIB], rr[SIB], nx[SIB], ths[SIB];
-    __shared__ int order[SIB];
+    __shared__ double th[BW], rr[BW], nx[BW], ths[BW];
+    __shared__ int order[BW];
     __shared__ int s_svp, s_conv;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;      // warp = seat 0..15
-    constexpr int m = SIB / 2;
+    constexpr int m = BW / 2;
     double xp[E], xq[E], vp[E], vq[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -154,11 +155,13 @@ si_jacobi_kernel(const double* __restrict__ X, double* __restrict__ Q, int n, do
         vp[e] = ok ? Q[(int64_t)(2 * warp) * n + i] : 0.0;
         vq[e] = ok ? Q[(int64_t)(2 * warp + 1) * n + i] : 0.0;
     }
+    // pairs of two UNWANTED columns (|x|^2 < tau^4, i.e. Ritz value below tau^2) only need to stay well conditioned
+    const double wanted2 = tau2 < 1.0e150 ? 0.25 * tau2 * tau2 : 0.0;      // opnorm mode: tight everywhere
     int sweeps = 0;
     for (; sweeps < 30; ++sweeps) {
         int rotated = 0;
         for (int round = 0; round < 2 * m - 1; ++round) {
-            rotated |= rotate_pair<E>(xp, xq, vp, vq, tol_jac) ? 1 : 0;
+            rotated |= rotate_pair<E>(xp, xq, vp, vq, tol_jac, wanted2) ? 1 : 0;
             const int s = warp;
             int ts, tw, bs, bw;
             if (s == 0) { ts = 0; tw = 0; } else if (s == m - 1) { ts = m - 1; tw = 1; } else { ts = s + 1; tw = 0; }
@@ -215,21 +218,22 @@ si_jacobi_kernel(const double* __restrict__ X, double* __restrict__ Q, int n, do
         }
     }
     __syncthreads();
-    if (tid < SIB) {
+    if (tid < BW) {
         const double lj = th[tid];
         int rank = 0;
-        for (int k = 0; k < SIB; ++k) rank += (th[k] > lj) || (th[k] == lj && k < tid);
+        for (int k = 0; k < BW; ++k) rank += (th[k] > lj) || (th[k] == lj && k < tid);
         order[rank] = tid;
         ths[rank] = lj;
     }
     __syncthreads();
     if (tid == 0) {
         int svp = 0;
-        for (int i = 0; i < SIB; ++i) svp += (ths[i] >= tau2) ? 1 : 0;
+        for (int i = 0; i < BW; ++i) svp += (ths[i] >= tau2) ? 1 : 0;
         // only the WANTED pairs must be converged: Ritz values are lower bounds, so the count is >= svp whatever the
         // state of the unwanted ones (they track the flat bulk and converge arbitrarily slowly); "<= svp" is proven
         // by the squaring certificate.
-        int conv = (svp <= SIB - 2) ? 1 : 0;
+        if (svp < min_wanted) svp = min_wanted;       // top-k mode (opnorm: the dominant pair regardless of tau)
+        int conv = (svp <= BW - 2) ? 1 : 0;
         const int need = svp;
         const double lim = tol_res * fabs(ths[0]);
         for (int i = 0; i < need; ++i) conv &= (rr[order[i]] <= lim) ? 1 : 0;
@@ -238,7 +242,7 @@ si_jacobi_kernel(const double* __restrict__ X, double* __restrict__ Q, int n, do
         flags[3] += 1;
         flags[5] = sweeps;
         if (conv) { flags[0] = 1; flags[2] = svp; }
-        else if (svp > SIB - 2 || last_step) flags[1] = 1;
+        else if (svp > BW - 2 || last_step) flags[1] = 1;
     }
     __syncthreads();
     const int conv = s_conv;
@@ -247,7 +251,7 @@ si_jacobi_kernel(const double* __restrict__ X, double* __restrict__ Q, int n, do
     for (int which = 0; which < 2; ++which) {
         const int col = 2 * warp + which;
         int rank = 0;
-        for (int k = 0; k < SIB; ++k) rank = (order[k] == col) ? k : rank;
+        for (int k = 0; k < BW; ++k) rank = (order[k] == col) ? k : rank;
         const double nrm = nx[col];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -284,10 +288,10 @@ deflate_kernel(const double* __restrict__ G, int n, const double* __restrict__ Q
 
 // certificate + outputs of the fast path (single CTA)
 __global__ void __launch_bounds__(256)
-fast_finish_kernel(int n, int nsq, const double* __restrict__ f2, double tau2, double tau, int nukeA,
+fast_finish_kernel(int n, int nsq, const double* __restrict__ f2, double tau2, int top1, double tau, int nukeA,
                    const double* __restrict__ theta, const double* __restrict__ Qs, double* __restrict__ Qb,
                    double* __restrict__ Vs, double* __restrict__ lam, double* __restrict__ sigma,
-                   double* __restrict__ fvec, int* __restrict__ svp_out, int* __restrict__ flags) {
+                   double* __restrict__ fvec, int* __restrict__ svp_out, int* __restrict__ flags, int bw) {
     __shared__ int ok;
     if (threadIdx.x == 0) {
         int good = (flags[0] == 1 && flags[1] == 0) ? 1 : 0;
@@ -296,7 +300,9 @@ fast_finish_kernel(int n, int nsq, const double* __restrict__ f2, double tau2, d
             double u = 1.0;
             for (int j = nsq - 1; j >= 0; --j) u = sqrt(sqrt(f2[j + 1]) * u);
             const double bound = sqrt(f2[0]) * u;
-            good = (bound < tau2 * (1.0 - 1e-10)) ? 1 : 0;
+            // ALM step: nothing left above tau^2.  opnorm mode: nothing left above theta_1, i.e. theta_1 IS lambda_max.
+            const double thr = top1 ? theta[0] : tau2;
+            good = (bound < thr * (1.0 - 1e-10)) ? 1 : 0;
             if (!(bound == bound)) good = 0;
         }
         if (!good) flags[1] = 1;
@@ -307,14 +313,14 @@ fast_finish_kernel(int n, int nsq, const double* __restrict__ f2, double tau2, d
     if (!ok) return;
     const int svp = flags[2];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double l = i < SIB ? theta[i] : 0.0;
+        const double l = i < bw ? theta[i] : 0.0;
         const double sg = l > 0.0 ? sqrt(l) : 0.0;
         lam[i] = l;
         sigma[i] = sg;
         const bool keep = i < svp;
         fvec[i] = keep ? (nukeA ? (sg - tau) / sg : 1.0) : 0.0;
     }
-    for (int idx = threadIdx.x; idx < n * SIB; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n * bw; idx += blockDim.x) {
         const double v = Qs[idx];
         Vs[idx] = v;
         Qb[idx] = v;
@@ -355,14 +361,19 @@ __global__ void lmax_bounds_kernel(const double* __restrict__ f2, int nsq, int n
     bounds[1] = f0 * u;
 }
 
-template <int E>
-cudaError_t launch_si(const double* X, double* Q, int n, double tau2, double tol_jac, double tol_res, int last,
-                      double* theta, double* Qout, int* flags, cudaStream_t st) {
-    const size_t smem = (size_t)SIB * 2 * 32 * E * sizeof(double);
-    auto kern = si_jacobi_kernel<E>;
+__global__ void init_block_kernel(double* __restrict__ Qb, int n) {      // Qb = [e_1 ... e_32]
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * SIB; idx += gridDim.x * blockDim.x)
+        Qb[idx] = (idx % n == idx / n) ? 1.0 : 0.0;
+}
+
+template <int E, int BW>
+cudaError_t launch_si(const double* X, double* Q, int n, double tau2, int min_wanted, double tol_jac, double tol_res,
+                      int last, double* theta, double* Qout, int* flags, cudaStream_t st) {
+    const size_t smem = (size_t)BW * 2 * 32 * E * sizeof(double);
+    auto kern = si_jacobi_kernel<E, BW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<1, 512, smem, st>>>(X, Q, n, tau2, tol_jac, tol_res, last, theta, Qout, flags);
+    kern<<<1, 16 * BW, smem, st>>>(X, Q, n, tau2, min_wanted, tol_jac, tol_res, last, theta, Qout, flags);
     return cudaGetLastError();
 }
 
@@ -417,25 +428,39 @@ cudaError_t launch_copy_block(const double* Vs, int n, double* Qb, const int* fl
     return cudaGetLastError();
 }
 
+cudaError_t launch_init_block(double* Qb, int n, cudaStream_t st, int64_t* launches) {
+    init_block_kernel<<<8, 256, 0, st>>>(Qb, n);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
-                            double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches) {
+                            double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1,
+                            int bw) {
+    if (bw != 16) bw = SIB;
     constexpr int NSI = 12;      // subspace-iteration steps attempted before falling back (skipped launches exit at once)
     constexpr int NSQ = 6;       // squarings of the certificate: bound within n^(1/128) of lambda_max
     cudaError_t e;
-    const double tau2 = tau * tau;
+    const double tau2 = top1 ? 1.0e300 : tau * tau;
+    const int min_wanted = top1 ? 1 : 0;
     const double tol_jac = 1.0e-15 * sqrt((double)n);
     const double tol_res = 4.0e-14;
     if ((e = cudaMemsetAsync(w.f2, 0, (16 + 8) * sizeof(double), st)) != cudaSuccess) return e;   // f2 + flags
-    if ((e = cudaMemcpyAsync(w.Qwork, w.Qb, (size_t)n * SIB * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(w.Qwork, w.Qb, (size_t)n * bw * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
         return e;
     const dim3 gx((n + AT - 1) / AT, 1);
     for (int it = 0; it < NSI; ++it) {
         // X = G' Q = G Q   (skipped once converged / failed)
-        atb_kernel<<<gx, 256, 0, st>>>(G, n, w.Qwork, n, n, n, SIB, nullptr, w.X, n, 0, nullptr, w.flags, 0);
+        atb_kernel<<<gx, 256, 0, st>>>(G, n, w.Qwork, n, n, n, bw, nullptr, w.X, n, 0, nullptr, w.flags, 0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         const int last = (it == NSI - 1) ? 1 : 0;
-        if (n <= 128) e = launch_si<4>(w.X, w.Qwork, n, tau2, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
-        else e = launch_si<8>(w.X, w.Qwork, n, tau2, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+        if (bw == 16) {
+            if (n <= 128) e = launch_si<4, 16>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+            else e = launch_si<8, 16>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+        } else {
+            if (n <= 128) e = launch_si<4, 32>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+            else e = launch_si<8, 32>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+        }
         if (e != cudaSuccess) return e;
     }
     deflate_kernel<<<(unsigned)(((int64_t)n * n + 255) / 256), 256, 0, st>>>(G, n, w.Qout, w.theta, w.flags, w.Ca,
@@ -450,8 +475,8 @@ cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFa
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         double* tmp = cin; cin = cout; cout = tmp;
     }
-    fast_finish_kernel<<<1, 256, 0, st>>>(n, NSQ, w.f2, tau2, tau, nukeA, w.theta, w.Qout, w.Qb, Vs, lam, sigma, fvec,
-                                          svp, w.flags);
+    fast_finish_kernel<<<1, 256, 0, st>>>(n, NSQ, w.f2, tau2, top1, tau, nukeA, w.theta, w.Qout, w.Qb, Vs, lam, sigma, fvec,
+                                          svp, w.flags, bw);
     if (launches) *launches += 2 * NSI + 1 + NSQ + 1;
     return cudaGetLastError();
 }

@@ -42,7 +42,13 @@ cudaError_t launch_gram_reduce(const double* partial, int nsplit, int nblk, int 
 // TMA-fed SYRK for a materialised dense X (syrk_tma.cu): 128 x 128 blocks, 16-row boxes, 4-stage mbarrier ring
 constexpr int kSyrkBlk = 128;
 constexpr int kEigMaxN = 512;
-struct SyrkPlan { int nb; int nblk; int nsplit; int ntiles; size_t partial_bytes; };
+struct SyrkPlan {
+    int nb, nblk, nsplit, ntiles, ncta;     // 128-blocks per dimension, upper-triangular blocks, -, 32-row tiles, CTAs
+    int nsplit_blk[10];                     // row splits (CTAs) of every block, proportional to its cost
+    int cta_begin[11];                      // first CTA of every block
+    int part_off[10];                       // first partial slot of every block
+    size_t partial_bytes;
+};
 bool syrk_tma_eligible(const double* X, int64_t M, int64_t N, int64_t ld);
 SyrkPlan syrk_plan(int64_t M, int64_t N, int sm_count);
 cudaError_t launch_syrk_tma(const double* X, int64_t M, int64_t N, int64_t ld, const SyrkPlan& plan, double* partial,
@@ -83,8 +89,12 @@ struct EigFastWork {
 size_t eig_fast_work_doubles(int n);
 bool eig_fast_supported(int n);
 EigFastWork eig_fast_carve(double* base, int n);
+// top1 != 0: "opnorm mode" -- only the dominant eigenpair is wanted and the certificate proves theta_1 = lambda_max.
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
-                            double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches);
+                            double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1 = 0,
+                            int bw = 32);   // bw: width of the iterated block (16 or 32 columns of Qb)
+// Qb = first 32 unit vectors (cold start of the subspace iteration)
+cudaError_t launch_init_block(double* Qb, int n, cudaStream_t st, int64_t* launches);
 // bounds[0] <= lambda_max(G) <= bounds[1] (device doubles) for a symmetric PSD n x n G by 10 normalised squarings
 // (bracket ratio n^(1/2048)).  Ca, Cb: n x n scratch, f2: 16 doubles scratch.
 cudaError_t launch_lmax_bounds(const double* G, int n, double* Ca, double* Cb, double* f2, double* bounds,

@@ -271,6 +271,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     }
     bool have_q = false;
     bool last_was_fast = false;
+    int cur_bw = 16;
     // exact stop test: Z is materialised by the epilogue when the Frobenius bracket is expected to be undecided, its
     // Gram runs on the TMA SYRK kernel and lambda_max is bracketed by repeated squaring
     DevBuf bZ, bSq;
@@ -306,7 +307,17 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
         CK(launch_maxabs(D, hankel, M, N, dscal + 1, sms, st, L));                       // norm(Y, Inf)   :178
         CKR(allreduce(h, dscal + 1, 1, kNcclMax));
-        CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));                         // opnorm(Y)      :177
+        // opnorm(Y) (:177) needs only lambda_max(D'D): dominant-subspace iteration from a cold start with a
+        // certificate that theta_1 is the largest eigenvalue; the full Jacobi is the fallback
+        if (fast_ok) {
+            CK(launch_init_block(fw.Qb, n, st, L));
+            CK(launch_eig_fast(G, n, 0.0, 1, fw, lam, Vs, sigma, fvec, dsvp, st, L, 1, 16));
+            CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
+            CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
+            have_q = true;
+        } else {
+            CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
+        }
     }
     CK(cudaMemcpyAsync(hp, lam, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hp + 1, dscal + 1, 8, cudaMemcpyDeviceToHost, st));
@@ -344,10 +355,14 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
         {
             Phase ph(h, TLSQ_PHASE_EIG);
+            // a 16-column block is enough while the rank estimate stays <= 10 (it must stay <= block - 2); widening
+            // the block needs an orthonormal 32-column basis, which the next full Jacobi provides
+            const int want_bw = svp_last <= 10 ? 16 : 32;
+            if (want_bw > cur_bw) { have_q = false; cur_bw = 32; }
             if (fast_ok && have_q) {
                 // dominant eigenpairs + certified count; the full Jacobi below only runs (device-side flag) when the
                 // fast path could not prove the count
-                CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L));
+                CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L, 0, cur_bw));
                 CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
                 CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L, fw.flags));   // :198
                 CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));

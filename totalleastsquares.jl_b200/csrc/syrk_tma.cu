@@ -21,9 +21,12 @@ namespace tlsq {
 namespace {
 
 constexpr int SB = kSyrkBlk;      // 128 output block edge
-constexpr int SR = 16;            // rows per TMA box / pipeline stage
-constexpr int SST = 4;            // pipeline stages
-constexpr int PANEL_BYTES = SB * SR * 8;   // 16 KB
+constexpr int SR = 16;            // rows per TMA box (128-byte inner extent = the swizzle span)
+constexpr int SRS = 32;           // rows per pipeline stage (two boxes per panel)
+constexpr int SST = 3;            // pipeline stages
+constexpr int BOX_BYTES = SB * SR * 8;         // 16 KB
+constexpr int PANEL_BYTES = 2 * BOX_BYTES;     // 32 KB: 32 rows x 128 columns
+constexpr int STAGE_BYTES = 2 * PANEL_BYTES;   // 64 KB: panel i + panel j
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,18 +54,40 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
+// Warp -> output tiles.  Off-diagonal block: 4 x 2 warps, warp tile 32 x 64.  Diagonal block: only the 10 upper
+// 32 x 32 tiles are computed -- two warps own a 32 x 64 strip of row 0, six warps own one 32 x 32 tile each, placed
+// so that the four SM sub-partitions carry 3,3,2,2 tile units (a diagonal block costs 3/4 of an off-diagonal one and
+// gets proportionally fewer CTAs, see syrk_plan).
+__device__ __forceinline__ void warp_tiles(bool diag, int warp, int& a0, int& b0, int& nn) {
+    if (!diag) { a0 = 32 * (warp & 3); b0 = 64 * (warp >> 2); nn = 8; return; }
+    switch (warp) {
+        case 0: a0 = 0;  b0 = 0;  nn = 8; break;
+        case 1: a0 = 0;  b0 = 64; nn = 8; break;
+        case 2: a0 = 32; b0 = 32; nn = 4; break;
+        case 3: a0 = 32; b0 = 64; nn = 4; break;
+        case 4: a0 = 32; b0 = 96; nn = 4; break;
+        case 5: a0 = 64; b0 = 64; nn = 4; break;
+        case 6: a0 = 64; b0 = 96; nn = 4; break;
+        default: a0 = 96; b0 = 96; nn = 4; break;
+    }
+}
+
 __global__ void __launch_bounds__(256, 1)
-syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ partial, int nb, int ntiles) {
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ partial, const SyrkPlan plan) {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ uint64_t full_bar[SST];
     // 1024-byte alignment required by the 128B swizzle pattern
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
+    int blk = 0;
+    while (blk + 1 < plan.nblk && (int)blockIdx.x >= plan.cta_begin[blk + 1]) ++blk;
+    const int split = blockIdx.x - plan.cta_begin[blk];
+    const int nsplit = plan.nsplit_blk[blk];
     int bi = 0, bj = 0;
     {
-        int rem = blockIdx.x;
-        for (bi = 0; bi < nb; ++bi) {
-            const int cnt = nb - bi;
+        int rem = blk;
+        for (bi = 0; bi < plan.nb; ++bi) {
+            const int cnt = plan.nb - bi;
             if (rem < cnt) { bj = bi + rem; break; }
             rem -= cnt;
         }
@@ -70,8 +95,8 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
     const bool diag = (bi == bj);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wi = warp & 3, wj = warp >> 2;          // warp tile rows(i) [32wi, +32), cols(j) [64wj, +64)
-    const bool active = !(diag && (32 * wi >= 64 * wj + 64));
+    int a0, b0, nn;
+    warp_tiles(diag, warp, a0, b0, nn);
 
     if (tid == 0) {
 #pragma unroll
@@ -80,16 +105,20 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
     }
     __syncthreads();
 
-    const int nmy = (ntiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;   // k-tiles of this CTA
-    const uint32_t stage_bytes = diag ? PANEL_BYTES : 2 * PANEL_BYTES;
+    const int nmy = (plan.ntiles - split + nsplit - 1) / nsplit;       // 32-row tiles of this CTA
+    const uint32_t stage_tx = diag ? PANEL_BYTES : STAGE_BYTES;
 
     auto issue = [&](int i) {
         const int s = i % SST;
-        const int kt = blockIdx.y + i * gridDim.y;
-        uint8_t* st = base + (size_t)s * 2 * PANEL_BYTES;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_2d(st, &tmap, kt * SR, bi * SB, &full_bar[s]);
-        if (!diag) tma_load_2d(st + PANEL_BYTES, &tmap, kt * SR, bj * SB, &full_bar[s]);
+        const int kt = split + i * nsplit;
+        uint8_t* st = base + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], stage_tx);
+        tma_load_2d(st, &tmap, kt * SRS, bi * SB, &full_bar[s]);
+        tma_load_2d(st + BOX_BYTES, &tmap, kt * SRS + SR, bi * SB, &full_bar[s]);
+        if (!diag) {
+            tma_load_2d(st + PANEL_BYTES, &tmap, kt * SRS, bj * SB, &full_bar[s]);
+            tma_load_2d(st + PANEL_BYTES + BOX_BYTES, &tmap, kt * SRS + SR, bj * SB, &full_bar[s]);
+        }
     };
     if (tid == 0) {
         for (int i = 0; i < SST && i < nmy; ++i) issue(i);
@@ -102,8 +131,8 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
         const int k = 2 * s4 + (t & 1) + 8 * (t >> 1);
         koff[s4] = (uint32_t)((((k >> 1) ^ g) << 4) | ((k & 1) << 3));
     }
-    const uint32_t a_col = (uint32_t)(32 * wi + g) * 128u;
-    const uint32_t b_col = (uint32_t)(64 * wj + g) * 128u;
+    const uint32_t a_col = (uint32_t)(a0 + g) * 128u;
+    const uint32_t b_col = (uint32_t)(b0 + g) * 128u;
 
     double acc[4][8][2];
 #pragma unroll
@@ -115,40 +144,61 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
         const int s = i % SST;
         const uint32_t parity = (uint32_t)((i / SST) & 1);
         mbar_wait(&full_bar[s], parity);
-        if (active) {
-            const uint8_t* pa = base + (size_t)s * 2 * PANEL_BYTES;
-            const uint8_t* pb = diag ? pa : pa + PANEL_BYTES;
+        const uint8_t* pa = base + (size_t)s * STAGE_BYTES;
+        const uint8_t* pb = diag ? pa : pa + PANEL_BYTES;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
                 double a[4], b[8];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
-                    a[mi] = *reinterpret_cast<const double*>(pa + a_col + (uint32_t)mi * 1024u + koff[s4]);
+                    a[mi] = *reinterpret_cast<const double*>(pa + half * BOX_BYTES + a_col + (uint32_t)mi * 1024u + koff[s4]);
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni)
-                    b[ni] = *reinterpret_cast<const double*>(pb + b_col + (uint32_t)ni * 1024u + koff[s4]);
+                    if (ni < nn)
+                        b[ni] = *reinterpret_cast<const double*>(pb + half * BOX_BYTES + b_col + (uint32_t)ni * 1024u + koff[s4]);
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+                for (int ni = 0; ni < 8; ++ni)
+                    if (ni < nn) {
 #pragma unroll
-                    for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                        for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    }
             }
         }
         __syncthreads();                               // every warp is done with stage s -> refill it
         if (tid == 0 && i + SST < nmy) issue(i + SST);
     }
 
-    double* P = partial + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (SB * SB);
-    if (active) {
+    double* P = partial + ((size_t)plan.part_off[blk] + split) * (SB * SB);
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
-                const int il = 32 * wi + 8 * mi + g;
-                const int jl = 64 * wj + 8 * ni + 2 * t;
+        for (int ni = 0; ni < 8; ++ni)
+            if (ni < nn) {
+                const int il = a0 + 8 * mi + g;
+                const int jl = b0 + 8 * ni + 2 * t;
                 P[jl * SB + il] = acc[mi][ni][0];
                 P[(jl + 1) * SB + il] = acc[mi][ni][1];
             }
-    }
+}
+
+// G[i,j] = G[j,i] = sum over the splits of block(i,j), fixed order; diagonal blocks only hold their upper 32-tiles
+__global__ void syrk_reduce_kernel(const double* __restrict__ partial, const SyrkPlan plan, int N, double* __restrict__ G) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * N) return;
+    int i = (int)(idx % N), j = (int)(idx / N);
+    if (i > j) return;
+    const int bi = i / SB, bj = j / SB;
+    int il = i % SB, jl = j % SB;
+    if (bi == bj && (il >> 5) > (jl >> 5)) return;      // cannot happen for i <= j; kept for clarity
+    const int blk = bi * plan.nb - (bi * (bi - 1)) / 2 + (bj - bi);
+    const double* p = partial + (size_t)plan.part_off[blk] * (SB * SB) + jl * SB + il;
+    double sum = 0.0;
+    const int ns = plan.nsplit_blk[blk];
+    for (int sp = 0; sp < ns; ++sp) sum += p[(size_t)sp * (SB * SB)];
+    G[(int64_t)j * N + i] = sum;
+    G[(int64_t)i * N + j] = sum;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -182,15 +232,39 @@ bool syrk_tma_eligible(const double* X, int64_t M, int64_t N, int64_t ld) {
 }
 
 SyrkPlan syrk_plan(int64_t M, int64_t N, int sm_count) {
-    SyrkPlan p;
+    SyrkPlan p = {};
     p.nb = (int)((N + SB - 1) / SB);
     p.nblk = p.nb * (p.nb + 1) / 2;
-    p.ntiles = (int)((M + SR - 1) / SR);
-    int ns = sm_count / p.nblk;
-    if (ns > p.ntiles) ns = p.ntiles;
-    if (ns < 1) ns = 1;
-    p.nsplit = ns;
-    p.partial_bytes = (size_t)p.nsplit * p.nblk * SB * SB * sizeof(double);
+    p.ntiles = (int)((M + SRS - 1) / SRS);
+    // CTAs per block proportional to the block's cost (off-diagonal 4 tile units per sub-partition, diagonal 3)
+    int ndiag = p.nb, noff = p.nblk - p.nb;
+    double unit = (double)sm_count / (4.0 * noff + 3.0 * ndiag);
+    int total = 0, blk = 0;
+    for (int bi = 0; bi < p.nb; ++bi)
+        for (int bj = bi; bj < p.nb; ++bj, ++blk) {
+            int ns = (int)((bi == bj ? 3.0 : 4.0) * unit);
+            if (ns < 1) ns = 1;
+            if (ns > p.ntiles) ns = p.ntiles;
+            p.nsplit_blk[blk] = ns;
+            total += ns;
+        }
+    // hand left-over SMs to the off-diagonal blocks first (they are the longest)
+    for (int pass = 0; pass < 4 && total < sm_count; ++pass) {
+        blk = 0;
+        for (int bi = 0; bi < p.nb && total < sm_count; ++bi)
+            for (int bj = bi; bj < p.nb && total < sm_count; ++bj, ++blk)
+                if (((bi != bj) == (pass % 2 == 0)) && p.nsplit_blk[blk] < p.ntiles) { ++p.nsplit_blk[blk]; ++total; }
+    }
+    int off = 0;
+    for (blk = 0; blk < p.nblk; ++blk) {
+        p.cta_begin[blk] = off;
+        p.part_off[blk] = off;
+        off += p.nsplit_blk[blk];
+    }
+    p.cta_begin[p.nblk] = off;
+    p.ncta = off;
+    p.nsplit = p.nsplit_blk[0];
+    p.partial_bytes = (size_t)off * SB * SB * sizeof(double);
     return p;
 }
 
@@ -207,20 +281,20 @@ cudaError_t launch_syrk_tma(const double* X, int64_t M, int64_t N, int64_t ld, c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)SST * 2 * PANEL_BYTES + 1024;
+    const size_t smem = (size_t)SST * STAGE_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid(plan.nblk, plan.nsplit);
-    syrk_tma_kernel<<<grid, 256, smem, st>>>(map, partial, plan.nb, plan.ntiles);
+    syrk_tma_kernel<<<plan.ncta, 256, smem, st>>>(map, partial, plan);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    e = launch_gram_reduce(partial, plan.nsplit, plan.nblk, plan.nb, SB, (int)N, G, st);
+    const int64_t nn = N * N;
+    syrk_reduce_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(partial, plan, (int)N, G);
     if (launches) *launches += 2;
-    return e;
+    return cudaGetLastError();
 }
 
 }  // namespace tlsq
