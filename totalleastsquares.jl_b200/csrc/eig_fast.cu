@@ -384,7 +384,8 @@ size_t eig_fast_work_doubles(int n) {
     return (size_t)4 * n * SIB + SIB + (size_t)2 * n * n + 16 + 8 + 16;
 }
 
-bool eig_fast_supported(int n) { return n > 64 && n <= 256; }
+bool eig_fast_supported(int n) { return n > 64 && n <= 512; }
+int eig_fast_max_block(int n) { return n <= 256 ? 32 : 16; }   // shared memory: block x 2 x n doubles must fit
 
 EigFastWork eig_fast_carve(double* base, int n) {
     EigFastWork w;
@@ -438,6 +439,7 @@ cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFa
                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1,
                             int bw) {
     if (bw != 16) bw = SIB;
+    if (n > 256) bw = 16;
     constexpr int NSI = 12;      // subspace-iteration steps attempted before falling back (skipped launches exit at once)
     constexpr int NSQ = 6;       // squarings of the certificate: bound within n^(1/128) of lambda_max
     cudaError_t e;
@@ -456,7 +458,8 @@ cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFa
         const int last = (it == NSI - 1) ? 1 : 0;
         if (bw == 16) {
             if (n <= 128) e = launch_si<4, 16>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
-            else e = launch_si<8, 16>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+            else if (n <= 256) e = launch_si<8, 16>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
+            else e = launch_si<16, 16>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
         } else {
             if (n <= 128) e = launch_si<4, 32>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);
             else e = launch_si<8, 32>(w.X, w.Qwork, n, tau2, min_wanted, tol_jac, tol_res, last, w.theta, w.Qout, w.flags, st);

@@ -73,7 +73,7 @@ size_t eig_work_doubles(int n);
 cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
                         int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag = nullptr);
 
-// Fast path (eig_fast.cu, 64 < n <= 256): warm-started block subspace iteration for the dominant eigenpairs +
+// Fast path (eig_fast.cu, 64 < n <= 512; 16-column block only above n = 256): warm-started block subspace iteration for the dominant eigenpairs +
 // a rigorous certificate of the count #{sigma >= tau}.  flags[1] != 0 afterwards means "fall back to launch_eigh".
 struct EigFastWork {
     double* Qb;      // n x 32 warm-start basis carried between ALM iterations
@@ -88,6 +88,7 @@ struct EigFastWork {
 };
 size_t eig_fast_work_doubles(int n);
 bool eig_fast_supported(int n);
+int eig_fast_max_block(int n);
 EigFastWork eig_fast_carve(double* base, int n);
 // top1 != 0: "opnorm mode" -- only the dominant eigenpair is wanted and the certificate proves theta_1 = lambda_max.
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,

@@ -359,7 +359,8 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             // the block needs an orthonormal 32-column basis, which the next full Jacobi provides
             const int want_bw = svp_last <= 10 ? 16 : 32;
             if (want_bw > cur_bw) { have_q = false; cur_bw = 32; }
-            if (fast_ok && have_q) {
+            const bool block_fits = cur_bw <= eig_fast_max_block(n);      // n > 256: only the 16-column block
+            if (fast_ok && have_q && block_fits) {
                 // dominant eigenpairs + certified count; the full Jacobi below only runs (device-side flag) when the
                 // fast path could not prove the count
                 CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L, 0, cur_bw));
