@@ -50,6 +50,16 @@ sg = np.sign(np.sum(Qo[a0:a1] * Qn, axis=0)); sg[sg == 0] = 1
 good = np.abs(Qn * sg - Qo[a0:a1]).max() < 1e-9 and inf["iters"] == its
 ok &= good
 print(f"[rank {rank}] rpca_ga iters {inf['iters']}/{its} maxdiff {np.abs(Qn * sg - Qo[a0:a1]).max():.1e} ok={good}", flush=True)
+# lowrankfilter: replicated signal, sharded Hankel rows
+y, yn = T.synth.sinusoid_np(4000, seed=2, noise=0.05)
+yd = torch.from_numpy(yn).to(dev)
+for (nn, lag) in [(100, 1), (37, 3)]:
+    yf, inf = T.lowrankfilter(yd, nn, lag=lag, return_info=True)
+    yo = O.lowrankfilter(yn, nn, lag=lag)
+    err = relF(yf.cpu().numpy(), yo)
+    good = err < 1e-9
+    ok &= good
+    print(f"[rank {rank}] lowrankfilter n={nn} lag={lag} iters {inf['iters']} rel {err:.1e} ok={good}", flush=True)
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("MGPU_CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)

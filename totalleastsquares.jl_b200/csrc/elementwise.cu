@@ -34,7 +34,7 @@ init_ya_kernel(const MatSrc D, int64_t M, int64_t N, double dual, double* __rest
         const double d = src_at<HANKEL>(D, row, col);
         const double y = __ddiv_rn(d, dual);                         // Y ./= dual_norm   (:181)
         Y[idx] = y;
-        A[idx] = 0.0;
+        if (A) A[idx] = 0.0;
         if (W) {
             double e, w;
             alm_ew(d, 0.0, y, im, eps, nonnegE, e, w);               // first SVT input   (:188-192)
@@ -107,6 +107,37 @@ unhankel_kernel(const double* __restrict__ A, int64_t K, int64_t L, int64_t lag,
     }
 }
 
+// sharded unhankel: this rank owns Hankel rows [r0, r0 + Kl); sums/counts of the anti-diagonals it touches
+__global__ void __launch_bounds__(256)
+unhankel_partial_kernel(const double* __restrict__ A, int64_t r0, int64_t Kl, int64_t L, int64_t lag, int64_t Ns,
+                        double* __restrict__ sum, double* __restrict__ cnt) {
+    const int64_t t_lo = r0 * lag, t_hi = (r0 + Kl - 1) * lag + L;          // [t_lo, t_hi)
+    for (int64_t tt = t_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tt < t_hi && tt < Ns;
+         tt += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        int64_t c = 0;
+        for (int64_t l = 0; l < L; ++l) {
+            const int64_t rem = tt - l;
+            if (rem < 0) break;
+            if (rem % lag) continue;
+            const int64_t k = rem / lag - r0;
+            if (k < 0 || k >= Kl) continue;
+            s += A[l * Kl + k];
+            ++c;
+        }
+        sum[tt] = s;
+        cnt[tt] = (double)c;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unhankel_divide_kernel(const double* __restrict__ sum, const double* __restrict__ cnt, int64_t Ns, double* __restrict__ y) {
+    for (int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tt < Ns; tt += (int64_t)gridDim.x * blockDim.x) {
+        const double c = cnt[tt];
+        y[tt] = sum[tt] / (c > 0.0 ? c : 1.0);                                 // y ./= max.(counts, 1)   (:66)
+    }
+}
+
 inline int stream_grid(int64_t total, int sm_count) {
     int64_t want = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count * 8;
@@ -166,6 +197,21 @@ cudaError_t launch_unhankel(const double* A, int64_t K, int64_t L, int64_t lag, 
                             cudaStream_t st, int64_t* launches) {
     const int grid = stream_grid(Ns, 148);
     unhankel_kernel<<<grid, 256, 0, st>>>(A, K, L, lag, Ns, y);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unhankel_partial(const double* A, int64_t r0, int64_t Kl, int64_t L, int64_t lag, int64_t Ns,
+                                    double* sum, double* cnt, cudaStream_t st, int64_t* launches) {
+    const int64_t span = (Kl - 1) * lag + L;
+    unhankel_partial_kernel<<<stream_grid(span, 148), 256, 0, st>>>(A, r0, Kl, L, lag, Ns, sum, cnt);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unhankel_divide(const double* sum, const double* cnt, int64_t Ns, double* y, cudaStream_t st,
+                                   int64_t* launches) {
+    unhankel_divide_kernel<<<stream_grid(Ns, 148), 256, 0, st>>>(sum, cnt, Ns, y);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -130,6 +130,13 @@ struct EpiArgs {
     double im, eps, mu;
     int nonnegA, nonnegE;
     double* zz;         // device scalar accumulator for ||Z||_F^2
+    // factored low-rank iterate (stream.cu): A_k = clamp(T_k V_k'), T: M x 32 (ld M), V: N x 32 (ld N).  When Tn != null
+    // the streaming epilogue reads A_{k-1} from (Tp, Vp, svp_prev) and writes T_k instead of the dense A_k: the dense
+    // A is never read or written inside the ALM loop (2 S less HBM traffic per iteration, 2 S less memory).
+    const double* Tp;
+    const double* Vp;
+    int svp_prev;
+    double* Tn;
 };
 cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_count, cudaStream_t st,
                             int64_t* launches);
@@ -137,15 +144,22 @@ cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_c
 // Streaming form of the epilogue (stream.cu) for a materialised W and svp <= kStreamMaxRank (svp known on the host):
 // T (M x 32 workspace) = W V_r diag(f), then one coalesced element-wise pass.  Needs a.Wn != nullptr.
 constexpr int kStreamMaxRank = 32;
-cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, double* T, int svp, bool hankel, int sm_count,
+cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count,
                                    cudaStream_t st, int64_t* launches);
+// can the factored form be used for this (N, svp, svp_prev)?  (two N x RP blocks of V must fit in shared memory)
+bool stream_factored_fits(int64_t N, int svp, int svp_prev);
+// dense helpers for the factored iterate:  A = clamp(T V')   and   Z = (D - A_k) - E_k  with A_{k-1}, A_k factored
+cudaError_t launch_fact_to_dense(const double* T, const double* V, int svp, int64_t M, int64_t N, int nonnegA,
+                                 double* A, int sm_count, cudaStream_t st, int64_t* launches);
+cudaError_t launch_z_from_factors(const EpiArgs& a, bool hankel, int svp, double* Z, int sm_count, cudaStream_t st,
+                                  int64_t* launches);
 
 // element-wise helpers ------------------------------------------------------------------------------
 // maxabs: *out = max |D_ij| (out must be zeroed);  init: Y = D / dual, A = 0
 cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, double* out, int sm_count,
                           cudaStream_t st, int64_t* launches);
 // W (optional) = SVT input of the first iteration: (D - E_1) + Y_0/mu_1 with A_0 = 0
-cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A,
+cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A /*nullable*/,
                            double* W, double im, double eps, int nonnegE, int sm_count, cudaStream_t st,
                            int64_t* launches);
 // E = soft_th((D - A) + Y/mu, lambda/mu) (+ clamp)
@@ -161,6 +175,13 @@ cudaError_t launch_hankel(const double* x, int64_t K, int64_t L, int64_t lag, do
                           int64_t* launches);
 cudaError_t launch_unhankel(const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, double* y,
                             cudaStream_t st, int64_t* launches);
+
+// row-sharded unhankel: partial anti-diagonal sums / counts of Hankel rows [r0, r0+Kl) (sum, cnt: Ns doubles, zeroed),
+// all-reduced by the caller, then divided
+cudaError_t launch_unhankel_partial(const double* A, int64_t r0, int64_t Kl, int64_t L, int64_t lag, int64_t Ns,
+                                    double* sum, double* cnt, cudaStream_t st, int64_t* launches);
+cudaError_t launch_unhankel_divide(const double* sum, const double* cnt, int64_t Ns, double* y, cudaStream_t st,
+                                   int64_t* launches);
 
 // Grassmann averages ----------------------------------------------------------------------------------
 enum GaMode : int {

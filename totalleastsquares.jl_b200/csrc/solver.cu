@@ -224,16 +224,36 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     SyrkPlan splan = syrk_plan(M, N, sms);
     const size_t part_bytes = use_w && splan.partial_bytes > plan.partial_bytes ? splan.partial_bytes
                                                                                  : plan.partial_bytes;
-    DevBuf bW, bT;
-    if (use_w) { CK(bW.alloc(mn * 8, st)); CK(bT.alloc((size_t)M * kStreamMaxRank * 8, st)); }
+    // Factored iterate: with W materialised the low-rank iterate is kept as A_k = clamp(T_k V_k') (T: M x 32,
+    // V: N x 32).  The dense A is then neither read nor written inside the loop; it is materialised only for the
+    // outputs, or for good (one-way switch to the dense representation) if the rank estimate ever exceeds 32.
+    static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
+    bool fact = use_w && !no_fact;
+    DevBuf bW, bT0, bT1, bV0, bV1;
+    if (use_w) CK(bW.alloc(mn * 8, st));
     double* Wbuf = use_w ? bW.as<double>() : nullptr;
-    double* Tbuf = use_w ? bT.as<double>() : nullptr;
+    double* Tb[2] = {nullptr, nullptr};
+    double* Vb[2] = {nullptr, nullptr};
+    int svpb[2] = {0, 0};
+    if (fact) {
+        CK(bT0.alloc((size_t)M * kStreamMaxRank * 8, st)); CK(bT1.alloc((size_t)M * kStreamMaxRank * 8, st));
+        CK(bV0.alloc((size_t)N * kStreamMaxRank * 8, st)); CK(bV1.alloc((size_t)N * kStreamMaxRank * 8, st));
+        Tb[0] = bT0.as<double>(); Tb[1] = bT1.as<double>(); Vb[0] = bV0.as<double>(); Vb[1] = bV1.as<double>();
+    }
 
     DevBuf bA0, bA1, bY0, bY1, bPart, bG, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
-    // A ping-pong: reuse the caller's A buffer as one side when given
-    double* Abuf[2];
-    if (o.A) Abuf[0] = o.A; else { CK(bA0.alloc(mn * 8, st)); Abuf[0] = bA0.as<double>(); }
-    CK(bA1.alloc(mn * 8, st)); Abuf[1] = bA1.as<double>();
+    // dense A ping-pong (reusing the caller's A buffer as one side when given); allocated lazily in factored mode
+    double* Abuf[2] = {nullptr, nullptr};
+    auto alloc_dense_a = [&]() -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (!Abuf[0]) {
+            if (o.A) Abuf[0] = o.A;
+            else { e = bA0.alloc(mn * 8, st); Abuf[0] = bA0.as<double>(); }
+        }
+        if (e == cudaSuccess && !Abuf[1]) { e = bA1.alloc(mn * 8, st); Abuf[1] = bA1.as<double>(); }
+        return e;
+    };
+    if (!fact) CK(alloc_dense_a());
     CK(bY0.alloc(mn * 8, st)); CK(bY1.alloc(mn * 8, st));
     double* Ybuf[2] = {bY0.as<double>(), bY1.as<double>()};
     CK(bPart.alloc(part_bytes, st));
@@ -330,7 +350,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     const double mubar = mu * 1.0e7;                                                     // :183
     {
         Phase ph(h, TLSQ_PHASE_INIT);
-        CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], Abuf[0], Wbuf, 1.0 / mu, p.lambda / mu, nonnegE,
+        CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], fact ? nullptr : Abuf[0], Wbuf, 1.0 / mu, p.lambda / mu, nonnegE,
                           sms, st, L));                                                  // Y ./= dual_norm :181
     }
 
@@ -377,7 +397,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         }
         // fused epilogue  (:188-192, 205-222)
         CK(cudaMemsetAsync(dscal, 0, 8, st));
-        EpiArgs ea;
+        EpiArgs ea = {};
         ea.D = D; ea.Ap = Abuf[cur]; ea.Yp = Ybuf[cur]; ea.An = Abuf[nxt]; ea.Yn = Ybuf[nxt];
         ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
         ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
@@ -397,10 +417,24 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         }
         {
             Phase ph(h, TLSQ_PHASE_EPILOGUE);
-            if (use_w && svp <= kStreamMaxRank)
-                CK(launch_stream_epilogue(ea, Wbuf, Tbuf, svp, hankel, sms, st, L));
-            else
+            if (fact && !stream_factored_fits(N, svp, svpb[cur])) {
+                // rank estimate beyond the factored kernels: materialise A_{k-1} and continue with the dense iterate
+                CK(alloc_dense_a());
+                CK(launch_fact_to_dense(Tb[cur], Vb[cur], svpb[cur], M, N, nonnegA, Abuf[cur], sms, st, L));
+                ea.Ap = Abuf[cur]; ea.An = Abuf[nxt];
+                fact = false;
+            }
+            if (fact) {
+                ea.Tp = Tb[cur]; ea.Vp = Vb[cur]; ea.svp_prev = svpb[cur]; ea.Tn = Tb[nxt];
+                CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
+                // V_k of this iterate (Vs is overwritten by the next eigen-decomposition)
+                CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
+                svpb[nxt] = svp;
+            } else if (use_w && svp <= kStreamMaxRank) {
+                CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
+            } else {
                 CK(launch_epilogue(ea, hankel, false, sms, st, L));
+            }
         }
         CKR(allreduce(h, dscal, 1, kNcclSum));
         CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
@@ -437,6 +471,11 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         if (need_exact) {
             Phase ph(h, TLSQ_PHASE_EXACT_COST);
             if (want_z) {
+                CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
+            } else if (fact) {
+                // the bracket was not predicted: rebuild Z_k from the factored iterates, then the same SYRK
+                if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
+                CK(launch_z_from_factors(ea, hankel, svp, Zbuf, sms, st, L));
                 CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
             } else {
                 gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;
@@ -480,8 +519,14 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     }
     // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
     // produced before A_k is copied there.
+    const double* Aprev_dense = Abuf[prev_idx];
+    if (fact && (o.E || o.U)) {
+        // factored iterate: A_{k-1} is materialised once into the (now free) W buffer
+        CK(launch_fact_to_dense(Tb[prev_idx], Vb[prev_idx], svpb[prev_idx], M, N, nonnegA, Wbuf, sms, st, L));
+        Aprev_dense = Wbuf;
+    }
     if (o.E)
-        CK(launch_compute_e(D, hankel, M, N, Abuf[prev_idx], Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
+        CK(launch_compute_e(D, hankel, M, N, Aprev_dense, Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
                             st, L));
     if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
@@ -493,16 +538,19 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
         CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
-        EpiArgs ea;
-        ea.D = D; ea.Ap = Abuf[prev_idx]; ea.Yp = Ybuf[prev_idx]; ea.An = nullptr; ea.Yn = nullptr;
+        EpiArgs ea = {};
+        ea.D = D; ea.Ap = Aprev_dense; ea.Yp = Ybuf[prev_idx]; ea.An = nullptr; ea.Yn = nullptr;
         ea.Wn = nullptr; ea.im_next = 0.0; ea.eps_next = 0.0; ea.Zout = nullptr;
         ea.Eout = nullptr; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
         ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last; ea.mu = 0.0; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
         ea.zz = dscal;
         CK(launch_epilogue(ea, hankel, true, sms, st, L));
     }
-    if (o.A && Abuf[last_idx] != o.A)
-        CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
+    if (o.A) {
+        if (fact) CK(launch_fact_to_dense(Tb[last_idx], Vb[last_idx], svpb[last_idx], M, N, nonnegA, o.A, sms, st, L));
+        else if (Abuf[last_idx] != o.A)
+            CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
+    }
     CK(cudaStreamSynchronize(st));
     if (o.sv) {
         int64_t sv = svp_last;                                                           // :199-204
@@ -633,11 +681,35 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
     if ((double)n > (double)Ns / 2.0)                                                    // @assert L <= N/2   :79
         return set_err(TLSQ_ERR_ARG, "L has to be less than N/2 = %g", (double)Ns / 2.0);
     if (lag > n) return set_err(TLSQ_ERR_ARG, "lag must be <= L");                       // :80
-    if (h->nranks > 1)
-        return set_err(TLSQ_ERR_UNSUPPORTED, "lowrankfilter: sharded signals are not implemented yet");
     const int64_t K = (Ns - n) / lag + 1;                                                // :81
     if (!(p.lambda > 0.0)) p.lambda = 1.0 / sqrt((double)(K > n ? K : n));               // :157
     cudaStream_t st = h->stream;
+    if (h->nranks > 1) {
+        // Row-sharded: every rank holds the (small) full signal and works on Hankel rows [r0, r1) through the same
+        // implicit index functor; only the n x n Gram, scalars and the anti-diagonal sums are all-reduced.
+        if (K < n || n > kEigMaxN)
+            return set_err(TLSQ_ERR_UNSUPPORTED, "lowrankfilter (sharded): needs K >= n and n <= %d", kEigMaxN);
+        const int64_t base = K / h->nranks, rem = K % h->nranks;
+        const int64_t r0 = h->rank * base + (h->rank < rem ? h->rank : rem);
+        const int64_t Kl = base + (h->rank < rem ? 1 : 0);
+        if (Kl < 1) return set_err(TLSQ_ERR_ARG, "lowrankfilter (sharded): fewer Hankel rows than ranks");
+        CKR(check_rpca_args(Kl, n, p));
+        DevBuf bAl, bSum;
+        CK(bAl.alloc((size_t)Kl * n * 8, st));
+        CK(bSum.alloc((size_t)2 * Ns * 8, st));
+        RpcaOut ol;
+        ol.A = bAl.as<double>(); ol.sv = sv; ol.iters_done = iters_done; ol.converged = converged; ol.hist = hist;
+        MatSrc srcl{y + r0 * lag, lag};
+        CKR(rpca_core(h, srcl, true, Kl, n, p, ol));
+        double* sum = bSum.as<double>();
+        double* cnt = sum + Ns;
+        CK(cudaMemsetAsync(sum, 0, (size_t)2 * Ns * 8, st));
+        CK(launch_unhankel_partial(ol.A, r0, Kl, n, lag, Ns, sum, cnt, st, &h->launches));
+        CKR(allreduce(h, sum, (size_t)2 * Ns, kNcclSum));
+        CK(launch_unhankel_divide(sum, cnt, Ns, yf, st, &h->launches));
+        CK(cudaStreamSynchronize(st));
+        return TLSQ_OK;
+    }
     DevBuf bA, bH;
     CK(bA.alloc((size_t)K * n * 8, st));
     RpcaOut o;

@@ -1,6 +1,7 @@
 // stream.cu -- the ALM epilogue as two streaming kernels (used when the SVT input W_k is materialised and svp <= 32):
 //
-//   alm_stream_kernel  every thread owns one matrix row:
+//   alm_stream_kernel  every thread owns one matrix row (FACT: the iterate A is kept FACTORED, A_k = clamp(T_k V_k'),
+//                      T: M x 32 -- the dense A is neither read nor written inside the loop):
 //                      loop 1  T[i,:] = (W_k[i,:] V_r) .* f      streaming read of W, svp FMAs per element
 //                      loop 2  one coalesced pass over D, A_{k-1}, Y_{k-1}:
 //                        A_k = clamp(sum_c T[i,c] V[j,c])                         src/robustPCA.jl:205-219
@@ -18,16 +19,31 @@ namespace tlsq {
 
 namespace {
 
-template <int RP, bool HANKEL>
+// sum_c t[c] * v[c] with v read from shared memory as 16-byte vectors (RP is a multiple of 8, v is 16-byte aligned)
+template <int RP>
+__device__ __forceinline__ double dot_rp(const double (&t)[RP > 0 ? RP : 1], const double* __restrict__ v) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < RP; c += 2) {
+        const double2 vv = *reinterpret_cast<const double2*>(v + c);
+        acc = fma(t[c], vv.x, acc);
+        acc = fma(t[c + 1], vv.y, acc);
+    }
+    return acc;
+}
+
+template <int RP, bool HANKEL, bool FACT>
 __global__ void __launch_bounds__(128)
 alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
-    extern __shared__ double Vsm[];            // [N][RP]
+    extern __shared__ double Vsm[];            // [N][RP]  (+ [N][RP] of V_{k-1} when FACT)
     __shared__ double fsm[RP > 0 ? RP : 1];
     const int N = (int)a.N;
+    double* Vpm = Vsm + (size_t)N * RP;
     if (threadIdx.x < RP) fsm[threadIdx.x] = (int)threadIdx.x < svp ? __ldg(a.fvec + threadIdx.x) : 0.0;
     for (int idx = threadIdx.x; idx < N * RP; idx += blockDim.x) {
         const int j = idx % N, c = idx / N;
         Vsm[j * RP + c] = c < svp ? __ldg(a.Vs + (int64_t)c * N + j) : 0.0;
+        if (FACT) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + j) : 0.0;
     }
     __syncthreads();
     double zz = 0.0;
@@ -35,39 +51,67 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.M;
          row += (int64_t)gridDim.x * blockDim.x) {
         // ---- T[row, :] = f .* (W[row, :] V_r): one streaming read of the materialised SVT input ----------------
+        // (software pipelined: the loads of the next column batch are in flight while the current one is consumed)
         double tr[RP > 0 ? RP : 1];
+        double tp[RP > 0 ? RP : 1];
 #pragma unroll
         for (int c = 0; c < RP; ++c) tr[c] = 0.0;
         if (RP > 0) {
             constexpr int UW = 8;
+            double wv[UW], wn[UW];
+#pragma unroll
+            for (int u = 0; u < UW; ++u) wv[u] = u < N ? __ldg(W + (int64_t)u * a.ldw + row) : 0.0;
             for (int j0 = 0; j0 < N; j0 += UW) {
-                double wv[UW];
 #pragma unroll
                 for (int u = 0; u < UW; ++u) {
-                    const int j = j0 + u;
-                    wv[u] = j < N ? __ldg(W + (int64_t)j * a.ldw + row) : 0.0;
+                    const int j = j0 + UW + u;
+                    wn[u] = j < N ? __ldg(W + (int64_t)j * a.ldw + row) : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < UW; ++u) {
                     const int j = j0 + u < N ? j0 + u : N - 1;
                     const double* v = Vsm + j * RP;
 #pragma unroll
-                    for (int c = 0; c < RP; ++c) tr[c] = fma(wv[u], v[c], tr[c]);
+                    for (int c = 0; c < RP; c += 2) {
+                        const double2 vv = *reinterpret_cast<const double2*>(v + c);
+                        tr[c] = fma(wv[u], vv.x, tr[c]);
+                        tr[c + 1] = fma(wv[u], vv.y, tr[c + 1]);
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < UW; ++u) wv[u] = wn[u];
             }
 #pragma unroll
             for (int c = 0; c < RP; ++c) tr[c] *= fsm[c];
+            if (FACT) {
+#pragma unroll
+                for (int c = 0; c < RP; ++c) {
+                    tp[c] = c < a.svp_prev ? __ldg(a.Tp + (int64_t)c * a.M + row) : 0.0;
+                    a.Tn[(int64_t)c * a.M + row] = tr[c];
+                }
+            }
+        }
+        double dv[UB], av[UB], yv[UB], dn[UB], an_[UB], yn_[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            dv[u] = av[u] = yv[u] = 0.0;
+            if (u < N) {
+                const int64_t off = (int64_t)u * a.ldw + row;
+                dv[u] = src_at<HANKEL>(a.D, row, u);
+                if (!FACT) av[u] = __ldg(a.Ap + off);
+                yv[u] = __ldg(a.Yp + off);
+            }
         }
         for (int j0 = 0; j0 < N; j0 += UB) {
-            double dv[UB], av[UB], yv[UB];
 #pragma unroll
             for (int u = 0; u < UB; ++u) {
-                const int j = j0 + u;
+                const int j = j0 + UB + u;
+                dn[u] = an_[u] = yn_[u] = 0.0;
                 if (j < N) {
                     const int64_t off = (int64_t)j * a.ldw + row;
-                    dv[u] = src_at<HANKEL>(a.D, row, j);
-                    av[u] = __ldg(a.Ap + off);
-                    yv[u] = __ldg(a.Yp + off);
+                    dn[u] = src_at<HANKEL>(a.D, row, j);
+                    if (!FACT) an_[u] = __ldg(a.Ap + off);
+                    yn_[u] = __ldg(a.Yp + off);
                 }
             }
 #pragma unroll
@@ -75,18 +119,22 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
                 const int j = j0 + u;
                 if (j < N) {
                     const int64_t off = (int64_t)j * a.ldw + row;
-                    const double d = dv[u], ap = av[u], yp = yv[u];
-                    double an = 0.0;
-                    const double* v = Vsm + j * RP;
-#pragma unroll
-                    for (int c = 0; c < RP; ++c) an = fma(tr[c], v[c], an);
+                    const double d = dv[u], yp = yv[u];
+                    double an = 0.0, ap = 0.0;
+                    if (RP > 0) an = dot_rp<RP>(tr, Vsm + j * RP);
                     if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;   // A .= max.(A, 0)   :218
+                    if (FACT) {                                                       // A_{k-1} from its factors
+                        if (RP > 0) ap = dot_rp<RP>(tp, Vpm + j * RP);
+                        if (a.nonnegA) ap = (__double_as_longlong(ap) > 0) ? ap : 0.0;
+                    } else {
+                        ap = av[u];
+                    }
                     double e, w;
                     alm_ew(d, ap, yp, a.im, a.eps, a.nonnegE, e, w);
                     const double z = __dsub_rn(__dsub_rn(d, an), e);                  // @. Z = D - A - E  :221
                     const double yn = __dadd_rn(yp, __dmul_rn(a.mu, z));              // @. Y = Y + mu*Z   :222
                     zz = fma(z, z, zz);
-                    a.An[off] = an;
+                    if (!FACT) a.An[off] = an;
                     a.Yn[off] = yn;
                     if (a.Eout) a.Eout[off] = e;
                     if (a.Zout) a.Zout[off] = z;
@@ -95,6 +143,8 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
                     a.Wn[off] = w2;
                 }
             }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) { dv[u] = dn[u]; av[u] = an_[u]; yv[u] = yn_[u]; }
         }
     }
     __shared__ double red[4];
@@ -104,39 +154,146 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
     if (threadIdx.x == 0) atomicAdd(a.zz, red[0] + red[1] + red[2] + red[3]);
 }
 
+// A = clamp(T V')  /  Z = (D - A_k) - E_k with both iterates factored (rare paths: outputs, missed Z prediction)
+template <int RP, bool HANKEL, bool ZMODE>
+__global__ void __launch_bounds__(128)
+fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* __restrict__ V, int svp,
+                  double* __restrict__ out) {
+    extern __shared__ double Vsm[];
+    const int N = (int)a.N;
+    double* Vpm = Vsm + (size_t)N * RP;
+    for (int idx = threadIdx.x; idx < N * RP; idx += blockDim.x) {
+        const int j = idx % N, c = idx / N;
+        Vsm[j * RP + c] = c < svp ? __ldg(V + (int64_t)c * N + j) : 0.0;
+        if (ZMODE) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + j) : 0.0;
+    }
+    __syncthreads();
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.M;
+         row += (int64_t)gridDim.x * blockDim.x) {
+        double tr[RP > 0 ? RP : 1], tp[(ZMODE && RP > 0) ? RP : 1];
+#pragma unroll
+        for (int c = 0; c < RP; ++c) {
+            tr[c] = c < svp ? __ldg(T + (int64_t)c * a.M + row) : 0.0;
+            if (ZMODE) tp[c] = c < a.svp_prev ? __ldg(a.Tp + (int64_t)c * a.M + row) : 0.0;
+        }
+        for (int j = 0; j < N; ++j) {
+            const int64_t off = (int64_t)j * a.ldw + row;
+            double an = 0.0;
+            const double* v = Vsm + j * RP;
+#pragma unroll
+            for (int c = 0; c < RP; ++c) an = fma(tr[c], v[c], an);
+            if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;
+            if (!ZMODE) { out[off] = an; continue; }
+            double ap = 0.0;
+            const double* vp = Vpm + j * RP;
+#pragma unroll
+            for (int c = 0; c < RP; ++c) ap = fma(tp[c], vp[c], ap);
+            if (a.nonnegA) ap = (__double_as_longlong(ap) > 0) ? ap : 0.0;
+            const double d = src_at<HANKEL>(a.D, row, j);
+            double e, w;
+            alm_ew(d, ap, __ldg(a.Yp + off), a.im, a.eps, a.nonnegE, e, w);
+            out[off] = __dsub_rn(__dsub_rn(d, an), e);
+        }
+    }
+}
+
+inline int rp_of(int svp) { return (svp + 7) & ~7; }
+
 template <int RP>
 cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count, cudaStream_t st) {
-    const size_t smem = (size_t)a.N * RP * sizeof(double);
-    cudaError_t e;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(alm_stream_kernel<RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(alm_stream_kernel<RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    const bool fact = a.Tn != nullptr;
+    const size_t smem = (size_t)a.N * RP * sizeof(double) * (fact ? 2 : 1);
     int64_t blocks = (a.M + 127) / 128;
     int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (hankel) alm_stream_kernel<RP, true><<<(unsigned)blocks, 128, smem, st>>>(a, W, svp);
-    else alm_stream_kernel<RP, false><<<(unsigned)blocks, 128, smem, st>>>(a, W, svp);
+    cudaError_t e = cudaSuccess;
+#define TLSQ_STREAM_LAUNCH(H, F)                                                                                  \
+    do {                                                                                                          \
+        auto kern = alm_stream_kernel<RP, H, F>;                                                                  \
+        if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(a, W, svp);                               \
+    } while (0)
+    if (hankel) { if (fact) TLSQ_STREAM_LAUNCH(true, true); else TLSQ_STREAM_LAUNCH(true, false); }
+    else        { if (fact) TLSQ_STREAM_LAUNCH(false, true); else TLSQ_STREAM_LAUNCH(false, false); }
+#undef TLSQ_STREAM_LAUNCH
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+template <int RP, bool ZMODE>
+cudaError_t launch_fact_rp(const EpiArgs& a, const double* T, const double* V, int svp, bool hankel, double* out,
+                           int sm_count, cudaStream_t st) {
+    const size_t smem = (size_t)a.N * RP * sizeof(double) * (ZMODE ? 2 : 1);
+    int64_t blocks = (a.M + 127) / 128;
+    int64_t cap = (int64_t)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaError_t e = cudaSuccess;
+    if (hankel) {
+        auto kern = fact_dense_kernel<RP, true, ZMODE>;
+        if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(a, T, V, svp, out);
+    } else {
+        auto kern = fact_dense_kernel<RP, false, ZMODE>;
+        if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(a, T, V, svp, out);
+    }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, double* T, int svp, bool hankel, int sm_count,
+bool stream_factored_fits(int64_t N, int svp, int svp_prev) {
+    if (svp > kStreamMaxRank || svp_prev > kStreamMaxRank) return false;
+    const int rp = rp_of(svp > svp_prev ? svp : svp_prev);
+    return (size_t)N * rp * 8 * 2 <= (size_t)200 * 1024;
+}
+
+cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count,
                                    cudaStream_t st, int64_t* launches) {
     cudaError_t e;
-    const int N = (int)a.N;
-    const int rp = (svp + 7) & ~7;
-    (void)T;
+    const bool fact = a.Tn != nullptr;
+    const int rp = rp_of(fact && a.svp_prev > svp ? a.svp_prev : svp);
     switch (rp) {
         case 0:  e = launch_stream_rp<0>(a, W, svp, hankel, sm_count, st); break;
         case 8:  e = launch_stream_rp<8>(a, W, svp, hankel, sm_count, st); break;
         case 16: e = launch_stream_rp<16>(a, W, svp, hankel, sm_count, st); break;
         case 24: e = launch_stream_rp<24>(a, W, svp, hankel, sm_count, st); break;
         default: e = launch_stream_rp<32>(a, W, svp, hankel, sm_count, st); break;
+    }
+    if (launches) *launches += 1;
+    return e;
+}
+
+cudaError_t launch_fact_to_dense(const double* T, const double* V, int svp, int64_t M, int64_t N, int nonnegA,
+                                 double* A, int sm_count, cudaStream_t st, int64_t* launches) {
+    EpiArgs a = {};
+    a.M = M; a.N = N; a.ldw = M; a.nonnegA = nonnegA;
+    cudaError_t e;
+    switch (rp_of(svp)) {
+        case 0:  e = launch_fact_rp<0, false>(a, T, V, svp, false, A, sm_count, st); break;
+        case 8:  e = launch_fact_rp<8, false>(a, T, V, svp, false, A, sm_count, st); break;
+        case 16: e = launch_fact_rp<16, false>(a, T, V, svp, false, A, sm_count, st); break;
+        case 24: e = launch_fact_rp<24, false>(a, T, V, svp, false, A, sm_count, st); break;
+        default: e = launch_fact_rp<32, false>(a, T, V, svp, false, A, sm_count, st); break;
+    }
+    if (launches) *launches += 1;
+    return e;
+}
+
+// a.{D, Yp, Tp, Vp, svp_prev, im, eps, nonnegA, nonnegE, M, N, ldw} describe iteration k's inputs; (a.Tn, a.Vs, svp) = A_k
+cudaError_t launch_z_from_factors(const EpiArgs& a, bool hankel, int svp, double* Z, int sm_count, cudaStream_t st,
+                                  int64_t* launches) {
+    cudaError_t e;
+    const int rp = rp_of(a.svp_prev > svp ? a.svp_prev : svp);
+    switch (rp) {
+        case 0:  e = launch_fact_rp<0, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 8:  e = launch_fact_rp<8, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 16: e = launch_fact_rp<16, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 24: e = launch_fact_rp<24, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        default: e = launch_fact_rp<32, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
     }
     if (launches) *launches += 1;
     return e;
