@@ -437,10 +437,12 @@ cudaError_t launch_init_block(double* Qb, int n, cudaStream_t st, int64_t* launc
 
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1,
-                            int bw) {
+                            int bw, int max_steps) {
     if (bw != 16) bw = SIB;
     if (n > 256) bw = 16;
-    constexpr int NSI = 12;      // subspace-iteration steps attempted before falling back (skipped launches exit at once)
+    // subspace-iteration steps attempted before falling back (launches after convergence exit at once, but each still
+    // costs a launch slot: the caller passes last iteration's step count + a margin)
+    const int NSI = max_steps < 2 ? 2 : (max_steps > 16 ? 16 : max_steps);
     constexpr int NSQ = 6;       // squarings of the certificate: bound within n^(1/128) of lambda_max
     cudaError_t e;
     const double tau2 = top1 ? 1.0e300 : tau * tau;

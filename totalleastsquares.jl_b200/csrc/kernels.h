@@ -93,7 +93,7 @@ EigFastWork eig_fast_carve(double* base, int n);
 // top1 != 0: "opnorm mode" -- only the dominant eigenpair is wanted and the certificate proves theta_1 = lambda_max.
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1 = 0,
-                            int bw = 32);   // bw: width of the iterated block (16 or 32 columns of Qb)
+                            int bw = 32, int max_steps = 12);   // bw: block width (16 / 32 columns of Qb); max_steps: subspace steps launched
 // Qb = first 32 unit vectors (cold start of the subspace iteration)
 cudaError_t launch_init_block(double* Qb, int n, cudaStream_t st, int64_t* launches);
 // bounds[0] <= lambda_max(G) <= bounds[1] (device doubles) for a symmetric PSD n x n G by 10 normalised squarings
@@ -151,6 +151,16 @@ bool stream_factored_fits(int64_t N, int svp, int svp_prev);
 // dense helpers for the factored iterate:  A = clamp(T V')   and   Z = (D - A_k) - E_k  with A_{k-1}, A_k factored
 cudaError_t launch_fact_to_dense(const double* T, const double* V, int svp, int64_t M, int64_t N, int nonnegA,
                                  double* A, int sm_count, cudaStream_t st, int64_t* launches);
+cudaError_t launch_final_from_factors(const EpiArgs& a, bool hankel, int svp, double* Wout, int sm_count,
+                                      cudaStream_t st, int64_t* launches);
+// C (M x N, ld M) = X (M x K, ld ldx) * B (K x N, ld K): TMA-free cp.async double-buffered DMMA GEMM (gemm.cu); used for
+// the left singular vectors U = W V diag(1/s) of the returned SVD (:238)
+cudaError_t launch_gemm_xb(const double* X, int64_t M, int K, int64_t ldx, const double* B, int N, double* C,
+                           cudaStream_t st, int64_t* launches);
+bool gemm_xb_eligible(const double* X, int64_t M, int K, int64_t ldx, int N);
+// B[:, c] = V[:, c] * (s_c > 0 ? 1/s_c : 0)
+cudaError_t launch_scale_cols_inv(const double* V, const double* sigma, int n, double* B, cudaStream_t st,
+                                  int64_t* launches);
 cudaError_t launch_z_from_factors(const EpiArgs& a, bool hankel, int svp, double* Z, int sm_count, cudaStream_t st,
                                   int64_t* launches);
 

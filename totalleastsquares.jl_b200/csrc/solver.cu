@@ -292,6 +292,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     bool have_q = false;
     bool last_was_fast = false;
     int cur_bw = 16;
+    int si_budget = 12;           // subspace steps launched per iteration: last iteration's count + margin
     // exact stop test: Z is materialised by the epilogue when the Frobenius bracket is expected to be undecided, its
     // Gram runs on the TMA SYRK kernel and lambda_max is bracketed by repeated squaring
     DevBuf bZ, bSq;
@@ -383,7 +384,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             if (fast_ok && have_q && block_fits) {
                 // dominant eigenpairs + certified count; the full Jacobi below only runs (device-side flag) when the
                 // fast path could not prove the count
-                CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L, 0, cur_bw));
+                CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L, 0, cur_bw, si_budget));
                 CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
                 CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L, fw.flags));   // :198
                 CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
@@ -412,8 +413,15 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         if (use_w) {
             // the streaming epilogue is specialised on the rank: fetch svp now (one short extra host sync)
             CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
+            if (fast_ok && last_was_fast) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             memcpy(&svp, hp + 1, 4);
+            if (fast_ok && last_was_fast) {
+                int fl[4];
+                memcpy(fl, hp + 8, 16);
+                // converged in fl[3] steps: budget that + 3 next time; a fallback resets the budget
+                si_budget = fl[1] ? 12 : fl[3] + 3;
+            }
         }
         {
             Phase ph(h, TLSQ_PHASE_EPILOGUE);
@@ -517,14 +525,43 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
         CK(launch_svt_post(lam, n, im_last, nukeA, sigma, fvec, dsvp, st, L));
     }
+    if (fact) {
+        // Factored iterate: ONE pass produces A_k, E_k and (for U) the last SVT input W_k from
+        // (T_{k-1}, V_{k-1}, Y_{k-1}) and (T_k, V_k); W_k lands in the W buffer, which is free now.
+        if (o.A || o.E || o.U) {
+            EpiArgs fa = {};
+            fa.D = D; fa.Yp = Ybuf[prev_idx]; fa.Tp = Tb[prev_idx]; fa.Vp = Vb[prev_idx]; fa.svp_prev = svpb[prev_idx];
+            fa.Tn = Tb[last_idx]; fa.Vs = Vb[last_idx]; fa.An = o.A; fa.Eout = o.E; fa.M = M; fa.N = N; fa.ldw = M;
+            fa.im = im_last; fa.eps = eps_last; fa.nonnegA = nonnegA; fa.nonnegE = nonnegE;
+            CK(launch_final_from_factors(fa, hankel, svpb[last_idx], o.U ? Wbuf : nullptr, sms, st, L));
+        }
+        if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
+        if (o.U) {
+            // U = W_k V diag(1/s): DMMA GEMM (gemm.cu); odd shapes take the fused tile kernel on a dense A_{k-1}
+            if (gemm_xb_eligible(Wbuf, M, n, M, n)) {
+                CK(launch_scale_cols_inv(Vs, sigma, n, sqA, st, L));
+                CK(launch_gemm_xb(Wbuf, M, n, M, sqA, n, o.U, st, L));
+            } else {
+                if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
+                CK(launch_fact_to_dense(Tb[prev_idx], Vb[prev_idx], svpb[prev_idx], M, N, nonnegA, Zbuf, sms, st, L));
+                std::vector<double> hs(n);
+                CK(cudaMemcpyAsync(hs.data(), sigma, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
+                CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
+                EpiArgs ea = {};
+                ea.D = D; ea.Ap = Zbuf; ea.Yp = Ybuf[prev_idx]; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M;
+                ea.Vs = Vs; ea.fvec = fvec; ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last;
+                ea.nonnegA = nonnegA; ea.nonnegE = nonnegE; ea.zz = dscal;
+                CK(launch_epilogue(ea, hankel, true, sms, st, L));
+            }
+        }
+    } else {
     // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
     // produced before A_k is copied there.
     const double* Aprev_dense = Abuf[prev_idx];
-    if (fact && (o.E || o.U)) {
-        // factored iterate: A_{k-1} is materialised once into the (now free) W buffer
-        CK(launch_fact_to_dense(Tb[prev_idx], Vb[prev_idx], svpb[prev_idx], M, N, nonnegA, Wbuf, sms, st, L));
-        Aprev_dense = Wbuf;
-    }
     if (o.E)
         CK(launch_compute_e(D, hankel, M, N, Aprev_dense, Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
                             st, L));
@@ -546,10 +583,8 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         ea.zz = dscal;
         CK(launch_epilogue(ea, hankel, true, sms, st, L));
     }
-    if (o.A) {
-        if (fact) CK(launch_fact_to_dense(Tb[last_idx], Vb[last_idx], svpb[last_idx], M, N, nonnegA, o.A, sms, st, L));
-        else if (Abuf[last_idx] != o.A)
-            CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
+    if (o.A && Abuf[last_idx] != o.A)
+        CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
     }
     CK(cudaStreamSynchronize(st));
     if (o.sv) {

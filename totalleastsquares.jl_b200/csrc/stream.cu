@@ -155,7 +155,7 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
 }
 
 // A = clamp(T V')  /  Z = (D - A_k) - E_k with both iterates factored (rare paths: outputs, missed Z prediction)
-template <int RP, bool HANKEL, bool ZMODE>
+template <int RP, bool HANKEL, int ZMODE>
 __global__ void __launch_bounds__(128)
 fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* __restrict__ V, int svp,
                   double* __restrict__ out) {
@@ -183,7 +183,7 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
 #pragma unroll
             for (int c = 0; c < RP; ++c) an = fma(tr[c], v[c], an);
             if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;
-            if (!ZMODE) { out[off] = an; continue; }
+            if (ZMODE == 0) { out[off] = an; continue; }
             double ap = 0.0;
             const double* vp = Vpm + j * RP;
 #pragma unroll
@@ -192,7 +192,13 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
             const double d = src_at<HANKEL>(a.D, row, j);
             double e, w;
             alm_ew(d, ap, __ldg(a.Yp + off), a.im, a.eps, a.nonnegE, e, w);
-            out[off] = __dsub_rn(__dsub_rn(d, an), e);
+            if (ZMODE == 1) {
+                out[off] = __dsub_rn(__dsub_rn(d, an), e);
+            } else {                                    // final outputs of the solve (:238): A_k, E_k and the last W
+                if (a.An) a.An[off] = an;
+                if (a.Eout) a.Eout[off] = e;
+                if (out) out[off] = w;
+            }
         }
     }
 }
@@ -221,7 +227,7 @@ cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, bool ha
     return cudaGetLastError();
 }
 
-template <int RP, bool ZMODE>
+template <int RP, int ZMODE>
 cudaError_t launch_fact_rp(const EpiArgs& a, const double* T, const double* V, int svp, bool hankel, double* out,
                            int sm_count, cudaStream_t st) {
     const size_t smem = (size_t)a.N * RP * sizeof(double) * (ZMODE ? 2 : 1);
@@ -273,11 +279,11 @@ cudaError_t launch_fact_to_dense(const double* T, const double* V, int svp, int6
     a.M = M; a.N = N; a.ldw = M; a.nonnegA = nonnegA;
     cudaError_t e;
     switch (rp_of(svp)) {
-        case 0:  e = launch_fact_rp<0, false>(a, T, V, svp, false, A, sm_count, st); break;
-        case 8:  e = launch_fact_rp<8, false>(a, T, V, svp, false, A, sm_count, st); break;
-        case 16: e = launch_fact_rp<16, false>(a, T, V, svp, false, A, sm_count, st); break;
-        case 24: e = launch_fact_rp<24, false>(a, T, V, svp, false, A, sm_count, st); break;
-        default: e = launch_fact_rp<32, false>(a, T, V, svp, false, A, sm_count, st); break;
+        case 0:  e = launch_fact_rp<0, 0>(a, T, V, svp, false, A, sm_count, st); break;
+        case 8:  e = launch_fact_rp<8, 0>(a, T, V, svp, false, A, sm_count, st); break;
+        case 16: e = launch_fact_rp<16, 0>(a, T, V, svp, false, A, sm_count, st); break;
+        case 24: e = launch_fact_rp<24, 0>(a, T, V, svp, false, A, sm_count, st); break;
+        default: e = launch_fact_rp<32, 0>(a, T, V, svp, false, A, sm_count, st); break;
     }
     if (launches) *launches += 1;
     return e;
@@ -289,11 +295,28 @@ cudaError_t launch_z_from_factors(const EpiArgs& a, bool hankel, int svp, double
     cudaError_t e;
     const int rp = rp_of(a.svp_prev > svp ? a.svp_prev : svp);
     switch (rp) {
-        case 0:  e = launch_fact_rp<0, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
-        case 8:  e = launch_fact_rp<8, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
-        case 16: e = launch_fact_rp<16, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
-        case 24: e = launch_fact_rp<24, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
-        default: e = launch_fact_rp<32, true>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 0:  e = launch_fact_rp<0, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 8:  e = launch_fact_rp<8, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 16: e = launch_fact_rp<16, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 24: e = launch_fact_rp<24, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        default: e = launch_fact_rp<32, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+    }
+    if (launches) *launches += 1;
+    return e;
+}
+
+// final outputs from the factored iterates in ONE pass: a.An <- A_k (a.Tn, a.Vs, svp), a.Eout <- E_k, Wout <- W_k (the
+// last SVT input, for U); a.{Tp, Vp, svp_prev, Yp, im, eps} describe iteration k's inputs.  Null outputs are skipped.
+cudaError_t launch_final_from_factors(const EpiArgs& a, bool hankel, int svp, double* Wout, int sm_count,
+                                      cudaStream_t st, int64_t* launches) {
+    cudaError_t e;
+    const int rp = rp_of(a.svp_prev > svp ? a.svp_prev : svp);
+    switch (rp) {
+        case 0:  e = launch_fact_rp<0, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
+        case 8:  e = launch_fact_rp<8, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
+        case 16: e = launch_fact_rp<16, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
+        case 24: e = launch_fact_rp<24, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
+        default: e = launch_fact_rp<32, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
     }
     if (launches) *launches += 1;
     return e;
