@@ -74,10 +74,12 @@ __device__ __forceinline__ void warp_tiles(bool diag, int warp, int& a0, int& b0
 
 __global__ void __launch_bounds__(256, 1)
 syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ partial, const SyrkPlan plan) {
-    extern __shared__ uint8_t smem_dyn[];
+    // 1024-byte alignment is required by the 128B swizzle pattern.  The pointer is NOT re-aligned with integer
+    // arithmetic: that would turn every fragment load into a generic LD instead of LDS.
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
     __shared__ uint64_t full_bar[SST];
-    // 1024-byte alignment required by the 128B swizzle pattern
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint8_t* base = smem_dyn;
+    if ((smem_u32(base) & 1023u) != 0u) __trap();
 
     int blk = 0;
     while (blk + 1 < plan.nblk && (int)blockIdx.x >= plan.cta_begin[blk + 1]) ++blk;
@@ -281,7 +283,7 @@ cudaError_t launch_syrk_tma(const double* X, int64_t M, int64_t N, int64_t ld, c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)SST * STAGE_BYTES + 1024;
+    const size_t smem = (size_t)SST * STAGE_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
