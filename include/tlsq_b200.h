@@ -71,7 +71,7 @@ int64_t     tlsq_launch_count(const tlsq_handle* h);
 
 /* optional device-side phase timing (CUDA events on the solve stream; off by default).  tlsq_set_profiling resets
  * the accumulators; tlsq_get_profile returns accumulated milliseconds and span counts per phase. */
-#define TLSQ_NUM_PHASES        8
+#define TLSQ_NUM_PHASES        9
 #define TLSQ_PHASE_GRAM        0   /* DMMA Gram of the SVT input (+ deterministic reduce)            */
 #define TLSQ_PHASE_EIG         1   /* n x n Jacobi eigensolver (+ warm-start GEMM, sort, shrink)     */
 #define TLSQ_PHASE_EPILOGUE    2   /* fused E / W / A / Z / Y pass                                    */
@@ -80,6 +80,7 @@ int64_t     tlsq_launch_count(const tlsq_handle* h);
 #define TLSQ_PHASE_FINALIZE    5   /* E, U, S, Vt outputs                                             */
 #define TLSQ_PHASE_ALLREDUCE   6   /* NCCL all-reduces                                                */
 #define TLSQ_PHASE_GA_SWEEP    7   /* Grassmann-average streaming sweep                               */
+#define TLSQ_PHASE_FUSED       8   /* one-pass ALM step: epilogue of iteration k + Gram of iteration k+1 */
 int tlsq_set_profiling(tlsq_handle* h, int on);
 int tlsq_get_profile(tlsq_handle* h, double* ms, int64_t* calls);
 

@@ -75,7 +75,7 @@ def launch_count(device: Optional[int] = None) -> int:
     return int(load().tlsq_launch_count(get_handle(device)))
 
 
-PHASES = ("gram", "eig", "epilogue", "exact_cost", "init", "finalize", "allreduce", "ga_sweep")
+PHASES = ("gram", "eig", "epilogue", "exact_cost", "init", "finalize", "allreduce", "ga_sweep", "fused")
 
 
 def set_profiling(on: bool, device: Optional[int] = None) -> None:
@@ -85,8 +85,8 @@ def set_profiling(on: bool, device: Optional[int] = None) -> None:
 
 def get_profile(device: Optional[int] = None) -> dict:
     """{phase: (milliseconds, spans)} accumulated since set_profiling(True)."""
-    ms = (C.c_double * 8)()
-    calls = (C.c_int64 * 8)()
+    ms = (C.c_double * len(PHASES))()
+    calls = (C.c_int64 * len(PHASES))()
     _cabi.check(load().tlsq_get_profile(get_handle(device), ms, calls))
     return {name: (float(ms[i]), int(calls[i])) for i, name in enumerate(PHASES)}
 

@@ -138,6 +138,62 @@ unhankel_divide_kernel(const double* __restrict__ sum, const double* __restrict_
     }
 }
 
+// Anti-diagonal sums of A = clamp(T V') over the local Hankel rows [r0, r0 + Kl), lag 1, WITHOUT materialising A
+// (unhankel of src/robustPCA.jl:28-39 applied to the factored iterate):
+//   sum[k] = sum_{j} clamp(T[k - j - r0, :] . V[j, :]),   0 <= k - j - r0 < Kl
+// A block owns 256 consecutive samples k; the 256 + n - 1 rows of T it needs are staged in shared memory.
+__global__ void __launch_bounds__(256)
+unhankel_factors_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ V, int rp, int nonnegA,
+                        int64_t r0, int64_t Kl, int n, int64_t Ns, double* __restrict__ sum) {
+    extern __shared__ double sm[];
+    const int span = 256 + n - 1;
+    double* Vsm = sm;                        // [n][rp]
+    double* Tsm = sm + (size_t)n * rp;       // [rp][span]
+    for (int idx = threadIdx.x; idx < n * rp; idx += 256) {
+        const int j = idx % n, c = idx / n;
+        Vsm[j * rp + c] = __ldg(V + (int64_t)c * n + j);
+    }
+    const int64_t nblk = (Ns + 255) / 256;
+    for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const int64_t kb = b * 256;
+        const int64_t ilo = kb - r0 - (n - 1);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < rp * span; idx += 256) {
+            const int q = idx % span, c = idx / span;
+            const int64_t i = ilo + q;
+            Tsm[c * span + q] = (i >= 0 && i < Kl) ? __ldg(T + (int64_t)c * ldt + i) : 0.0;
+        }
+        __syncthreads();
+        const int64_t k = kb + threadIdx.x;
+        if (k < Ns) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const int q = (int)threadIdx.x + (n - 1) - j;
+                const int64_t i = ilo + q;
+                if (i < 0 || i >= Kl) continue;
+                double av = 0.0;
+                for (int c = 0; c < rp; ++c) av = fma(Tsm[c * span + q], Vsm[j * rp + c], av);
+                if (nonnegA) av = (__double_as_longlong(av) > 0) ? av : 0.0;
+                s += av;
+            }
+            sum[k] = s;
+        }
+    }
+}
+
+// y[k] = sum[k] / #{(i, j): i + j = k, 0 <= i < K, 0 <= j < n}   (lag 1; the count is known in closed form)
+__global__ void __launch_bounds__(256)
+unhankel_divide_count_kernel(const double* __restrict__ sum, int64_t K, int64_t n, int64_t Ns, double* __restrict__ y) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < Ns; k += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = k;
+        if (n - 1 < c) c = n - 1;
+        if (K - 1 < c) c = K - 1;
+        if (K + n - 2 - k < c) c = K + n - 2 - k;
+        c = c < 0 ? 1 : c + 1;
+        y[k] = sum[k] / (double)c;
+    }
+}
+
 inline int stream_grid(int64_t total, int sm_count) {
     int64_t want = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count * 8;
@@ -212,6 +268,33 @@ cudaError_t launch_unhankel_partial(const double* A, int64_t r0, int64_t Kl, int
 cudaError_t launch_unhankel_divide(const double* sum, const double* cnt, int64_t Ns, double* y, cudaStream_t st,
                                    int64_t* launches) {
     unhankel_divide_kernel<<<stream_grid(Ns, 148), 256, 0, st>>>(sum, cnt, Ns, y);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unhankel_factors(const double* T, int64_t ldt, const double* V, int svp, int nonnegA, int64_t r0,
+                                    int64_t Kl, int64_t n, int64_t Ns, double* sum, int sm_count, cudaStream_t st,
+                                    int64_t* launches) {
+    if (svp < 1) return cudaMemsetAsync(sum, 0, (size_t)Ns * sizeof(double), st);     // A = 0
+    const int rp = svp;
+    const size_t smem = ((size_t)n * rp + (size_t)rp * (256 + n - 1)) * sizeof(double);
+    if (smem > (size_t)220 * 1024) return cudaErrorInvalidValue;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(unhankel_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    int64_t blocks = (Ns + 255) / 256;
+    if (blocks > (int64_t)sm_count * 4) blocks = (int64_t)sm_count * 4;
+    unhankel_factors_kernel<<<(unsigned)blocks, 256, smem, st>>>(T, ldt, V, rp, nonnegA, r0, Kl, (int)n, Ns, sum);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unhankel_divide_count(const double* sum, int64_t K, int64_t n, int64_t Ns, double* y, cudaStream_t st,
+                                         int64_t* launches) {
+    unhankel_divide_count_kernel<<<stream_grid(Ns, 148), 256, 0, st>>>(sum, K, n, Ns, y);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -164,6 +164,44 @@ cudaError_t launch_scale_cols_inv(const double* V, const double* sigma, int n, d
 cudaError_t launch_z_from_factors(const EpiArgs& a, bool hankel, int svp, double* Z, int sm_count, cudaStream_t st,
                                   int64_t* launches);
 
+
+// ----------------------------------------------------------------------------------------------------
+// Fused one-pass ALM step (fused.cu, n = 256): epilogue of iteration k + Gram of the SVT input of iteration k+1 in ONE
+// kernel (thread-block cluster pair per 32-row tile, DSMEM exchange, TMA staging, DMMA Gram).  W is never materialised.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kFusedN = 256;
+constexpr int kFusedMaxRank = 16;
+enum FusedGram : int {
+    FUSED_GRAM_WNEXT = 0,   // operand = W_{k+1} = (D - E_{k+1}) + Y_k/mu_{k+1}          (the normal step)
+    FUSED_GRAM_Z = 1,       // operand = Z_k = (D - A_k) - E_k                            (exact stop test, :225)
+    FUSED_GRAM_W = 2,       // operand = W_k from (D, A_{k-1}, Y_{k-1}); nothing written  (first iteration)
+    FUSED_GRAM_D = 3        // operand = D                                                (opnorm(D), :177)
+};
+struct FusedStripTab { uint8_t row[2][8][9]; uint8_t cs[2][8][9]; };
+struct FusedArgs {
+    MatSrc D;               // dense (TMA) or implicit Hankel signal with lag 1
+    const double* Vp;       // V_{k-1}: 256 x >= svp_prev (ld 256)
+    const double* Vs;       // V_k:     256 x >= svp      (ld 256)
+    const double* fvec;     // shrink factors of iteration k
+    int svp, svp_prev;
+    double* Yn; int64_t ldy;   // Y_k out (may alias Y_{k-1}: the pass is tile-local)
+    double* Tn; int64_t ldt;   // T_k out (compute_T) -- M x 32, ld ldt
+    int64_t M;
+    double im, eps, mu, im_next, eps_next;
+    int nonnegA, nonnegE;
+    int compute_T;          // 1: T_k = (W_k V_k) .* f is computed (and written to Tn); 0: T_k is read (Tn_given)
+    int write_Y;
+    int gram_of;            // FusedGram
+    double* partial;        // workspace, fused_partial_doubles(sm_count) doubles
+    double* zpart;          // workspace inside partial (set by the launcher)
+};
+size_t fused_partial_doubles(int sm_count);
+bool fused_eligible(const MatSrc& D, bool hankel, int64_t M, int64_t N);
+int fused_rank_pad(int svp, int svp_prev);
+// G (256 x 256) = Gram of the chosen operand; zz_out (nullable) = ||Z_k||_F^2
+cudaError_t launch_alm_fused(const FusedArgs& a, bool hankel, const double* Yp, const double* Tp, const double* Tn_given,
+                             double* G, double* zz_out, int sm_count, cudaStream_t st, int64_t* launches);
+
 // element-wise helpers ------------------------------------------------------------------------------
 // maxabs: *out = max |D_ij| (out must be zeroed);  init: Y = D / dual, A = 0
 cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, double* out, int sm_count,
@@ -192,6 +230,14 @@ cudaError_t launch_unhankel_partial(const double* A, int64_t r0, int64_t Kl, int
                                     double* sum, double* cnt, cudaStream_t st, int64_t* launches);
 cudaError_t launch_unhankel_divide(const double* sum, const double* cnt, int64_t Ns, double* y, cudaStream_t st,
                                    int64_t* launches);
+
+// unhankel of the FACTORED iterate A = clamp(T V') (lag 1): sum[k] over the local Hankel rows [r0, r0+Kl); every k in
+// [0, Ns) is written (0 where this shard does not contribute); the count is closed-form (divide_count)
+cudaError_t launch_unhankel_factors(const double* T, int64_t ldt, const double* V, int svp, int nonnegA, int64_t r0,
+                                    int64_t Kl, int64_t n, int64_t Ns, double* sum, int sm_count, cudaStream_t st,
+                                    int64_t* launches);
+cudaError_t launch_unhankel_divide_count(const double* sum, int64_t K, int64_t n, int64_t Ns, double* y, cudaStream_t st,
+                                         int64_t* launches);
 
 // Grassmann averages ----------------------------------------------------------------------------------
 enum GaMode : int {

@@ -198,6 +198,8 @@ struct RpcaParams {
 struct RpcaOut {
     double* A = nullptr;  double* E = nullptr;  double* U = nullptr;  double* S = nullptr;  double* Vt = nullptr;
     int64_t* sv = nullptr;  int64_t* iters_done = nullptr;  int32_t* converged = nullptr;  double* hist = nullptr;
+    // lowrankfilter: anti-diagonal sums of the final (factored) A over this shard's Hankel rows [uh_r0, uh_r0 + M)
+    double* uh_sum = nullptr;  int64_t uh_r0 = 0;  int64_t uh_Ns = 0;
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -218,20 +220,31 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // global row count (for the Frobenius bracket: d = min(M_global, N))
     double Mg = (double)M;
     GramPlan plan = gram_plan(M, N, sms);
-    // Fast path: the SVT input W_k is materialised by the previous epilogue and its Gram runs on the TMA-fed
-    // DMMA SYRK kernel (needs an even leading dimension for the 16-byte TMA stride and a tall enough matrix).
-    const bool use_w = syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), M, N, M);
+    // Three per-iteration pipelines, fastest first:
+    //   fused  (n = 256)  ONE kernel per iteration: epilogue of iteration k + Gram of the SVT input of iteration k+1
+    //                     (fused.cu); W is never materialised, the iterate is factored, 3 S of HBM traffic;
+    //   use_w             streaming epilogue that materialises W_{k+1} + TMA-fed DMMA SYRK of W (stream.cu, syrk_tma.cu);
+    //   generic           tile epilogue + Gram formed on the fly (epilogue.cu, gram.cu) for small / odd shapes.
+    const bool syrk_ok = syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), M, N, M);
     SyrkPlan splan = syrk_plan(M, N, sms);
-    const size_t part_bytes = use_w && splan.partial_bytes > plan.partial_bytes ? splan.partial_bytes
-                                                                                 : plan.partial_bytes;
-    // Factored iterate: with W materialised the low-rank iterate is kept as A_k = clamp(T_k V_k') (T: M x 32,
-    // V: N x 32).  The dense A is then neither read nor written inside the loop; it is materialised only for the
-    // outputs, or for good (one-way switch to the dense representation) if the rank estimate ever exceeds 32.
+    const size_t part_bytes = syrk_ok && splan.partial_bytes > plan.partial_bytes ? splan.partial_bytes
+                                                                                  : plan.partial_bytes;
+    // Factored iterate: the low-rank iterate is kept as A_k = clamp(T_k V_k') (T: M x 32, V: N x 32).  The dense A is
+    // then neither read nor written inside the loop; it is materialised only for the outputs, or for good (one-way
+    // switch to the dense representation) if the rank estimate ever exceeds 32.
     static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
-    bool fact = use_w && !no_fact;
-    DevBuf bW, bT0, bT1, bV0, bV1;
-    if (use_w) CK(bW.alloc(mn * 8, st));
-    double* Wbuf = use_w ? bW.as<double>() : nullptr;
+    bool fused = syrk_ok && !no_fact && fused_eligible(D, hankel, M, N);
+    bool use_w = syrk_ok && !fused;
+    bool fact = (use_w || fused) && !no_fact;
+    DevBuf bW, bT0, bT1, bV0, bV1, bFp;
+    double* Wbuf = nullptr;
+    auto ensure_w = [&]() -> cudaError_t {
+        if (Wbuf) return cudaSuccess;
+        cudaError_t e = bW.alloc(mn * 8, st);
+        Wbuf = bW.as<double>();
+        return e;
+    };
+    if (use_w) CK(ensure_w());
     double* Tb[2] = {nullptr, nullptr};
     double* Vb[2] = {nullptr, nullptr};
     int svpb[2] = {0, 0};
@@ -239,6 +252,15 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         CK(bT0.alloc((size_t)M * kStreamMaxRank * 8, st)); CK(bT1.alloc((size_t)M * kStreamMaxRank * 8, st));
         CK(bV0.alloc((size_t)N * kStreamMaxRank * 8, st)); CK(bV1.alloc((size_t)N * kStreamMaxRank * 8, st));
         Tb[0] = bT0.as<double>(); Tb[1] = bT1.as<double>(); Vb[0] = bV0.as<double>(); Vb[1] = bV1.as<double>();
+        CK(cudaMemsetAsync(Tb[0], 0, (size_t)M * kStreamMaxRank * 8, st));
+        CK(cudaMemsetAsync(Tb[1], 0, (size_t)M * kStreamMaxRank * 8, st));
+    }
+    FusedArgs fa = {};
+    if (fused) {
+        CK(bFp.alloc(fused_partial_doubles(sms) * 8, st));
+        fa.D = D; fa.M = M; fa.ldy = M; fa.ldt = M; fa.nonnegA = nonnegA; fa.nonnegE = nonnegE;
+        fa.partial = bFp.as<double>();
+        fa.zpart = fa.partial + (size_t)(sms / 2) * n * n;
     }
 
     DevBuf bA0, bA1, bY0, bY1, bPart, bG, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
@@ -254,16 +276,37 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         return e;
     };
     if (!fact) CK(alloc_dense_a());
-    CK(bY0.alloc(mn * 8, st)); CK(bY1.alloc(mn * 8, st));
-    double* Ybuf[2] = {bY0.as<double>(), bY1.as<double>()};
+    // Dual variable: two buffers (Y_{k-1} stays available for E_k, U and the exact stop test) unless the caller needs
+    // none of those outputs and two copies do not fit (lowrankfilter on very long signals): then Y is updated in place.
+    bool inplace_y = false;
+    if (fused && !o.E && !o.U && !o.S && !o.Vt) {
+        const char* env_ip = getenv("TLSQ_INPLACE_Y");      // test hook
+        if (env_ip) inplace_y = atoi(env_ip) != 0;
+        else {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+                uint64_t reserved = 0, used = 0;
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+                if (reserved > used) free_b += (size_t)(reserved - used);
+            }
+            const size_t need = 2 * mn * 8 + (size_t)4 << 30;
+            inplace_y = need > free_b;
+        }
+    }
+    CK(bY0.alloc(mn * 8, st));
+    if (!inplace_y) CK(bY1.alloc(mn * 8, st));
+    double* Ybuf[2] = {bY0.as<double>(), inplace_y ? bY0.as<double>() : bY1.as<double>()};
     CK(bPart.alloc(part_bytes, st));
-    CK(bG.alloc((size_t)n * n * 8, st)); CK(bG2.alloc((size_t)n * n * 8, st));
+    CK(bG.alloc(((size_t)n * n + 8) * 8, st)); CK(bG2.alloc(((size_t)n * n + 8) * 8, st));
     CK(bVs.alloc((size_t)n * n * 8, st)); CK(bVs2.alloc((size_t)n * n * 8, st));
     CK(bLam.alloc((size_t)n * 8, st)); CK(bLam2.alloc((size_t)n * 8, st));
     CK(bSig.alloc((size_t)n * 8, st)); CK(bF.alloc((size_t)n * 8, st));
     CK(bEig.alloc(eig_work_doubles(n) * 8, st));
     CK(bScal.alloc(16 * 8, st)); CK(bSvp.alloc(16, st));
-    double* G = bG.as<double>(); double* G2 = bG2.as<double>();
+    double* G = bG.as<double>(); double* G2 = bG2.as<double>();     // [n*n] Gram, [n*n] = ||Z||_F^2 (fused path)
     double* Vs = bVs.as<double>(); double* Vs2 = bVs2.as<double>();
     double* lam = bLam.as<double>(); double* lam2 = bLam2.as<double>();
     double* sigma = bSig.as<double>(); double* fvec = bF.as<double>();
@@ -321,10 +364,15 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = nonnegE;
     {
         Phase ph(h, TLSQ_PHASE_INIT);
-        if (use_w && !hankel && syrk_tma_eligible(D.p, M, N, D.ld))
+        if (syrk_ok && !hankel && syrk_tma_eligible(D.p, M, N, D.ld)) {
             CK(launch_syrk_tma(D.p, M, N, D.ld, splan, bPart.as<double>(), G, st, L));   // D'D
-        else
+        } else if (fused) {
+            FusedArgs f0 = fa;
+            f0.gram_of = FUSED_GRAM_D;
+            CK(launch_alm_fused(f0, hankel, nullptr, nullptr, nullptr, G, nullptr, sms, st, L));
+        } else {
             CK(launch_gram(gs, GRAM_D, hankel, plan, bPart.as<double>(), G, st, L));
+        }
         CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
         CK(launch_maxabs(D, hankel, M, N, dscal + 1, sms, st, L));                       // norm(Y, Inf)   :178
         CKR(allreduce(h, dscal + 1, 1, kNcclMax));
@@ -349,10 +397,19 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     const double d_norm = norm2;                                                         // :180
     double mu = 1.25 / norm2;                                                            // :182
     const double mubar = mu * 1.0e7;                                                     // :183
+    bool gram_ready = false;       // G already holds the Gram of this iteration's SVT input (fused path)
     {
         Phase ph(h, TLSQ_PHASE_INIT);
-        CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], fact ? nullptr : Abuf[0], Wbuf, 1.0 / mu, p.lambda / mu, nonnegE,
-                          sms, st, L));                                                  // Y ./= dual_norm :181
+        CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], fact ? nullptr : Abuf[0], fused ? nullptr : Wbuf,
+                          1.0 / mu, p.lambda / mu, nonnegE, sms, st, L));                // Y ./= dual_norm :181
+        if (fused) {
+            // Gram of the first SVT input W_1 = (D - E_1) + Y_0/mu_1 (A_0 = 0), formed on the fly
+            FusedArgs f1 = fa;
+            f1.gram_of = FUSED_GRAM_W; f1.im = 1.0 / mu; f1.eps = p.lambda / mu;
+            CK(launch_alm_fused(f1, hankel, Ybuf[0], nullptr, nullptr, G, nullptr, sms, st, L));
+            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+            gram_ready = true;
+        }
     }
 
     int cur = 0;
@@ -361,6 +418,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     int svp_last = 10;
     double im_last = 0.0, eps_last = 0.0;
     int prev_idx = 0, last_idx = 0;
+    static const bool dbg_eig = getenv("TLSQ_DEBUG_EIG") != nullptr;
 
     for (int64_t k = 1; k <= p.iters; ++k) {                                             // :186
         const int nxt = cur ^ 1;
@@ -368,12 +426,15 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         const double eps = p.lambda / mu;
         // SVT input Gram  (:188-194)
         gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = nullptr; gs.im = im; gs.eps = eps;
-        {
-            Phase ph(h, TLSQ_PHASE_GRAM);
-            if (use_w) CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), G, st, L));
-            else CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+        if (!gram_ready) {
+            {
+                Phase ph(h, TLSQ_PHASE_GRAM);
+                if (use_w) CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), G, st, L));
+                else CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+            }
+            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
         }
-        CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+        gram_ready = false;
         {
             Phase ph(h, TLSQ_PHASE_EIG);
             // a 16-column block is enough while the rank estimate stays <= 10 (it must stay <= block - 2); widening
@@ -396,22 +457,10 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                 last_was_fast = false;
             }
         }
-        // fused epilogue  (:188-192, 205-222)
-        CK(cudaMemsetAsync(dscal, 0, 8, st));
-        EpiArgs ea = {};
-        ea.D = D; ea.Ap = Abuf[cur]; ea.Yp = Ybuf[cur]; ea.An = Abuf[nxt]; ea.Yn = Ybuf[nxt];
-        ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
-        ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
-        ea.zz = dscal;
-        // will the Frobenius bracket [fro/sqrt(d), fro] probably straddle tol?  (fro shrinks by < 8x per iteration)
-        const bool want_z = use_w && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
-        if (want_z && !Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
-        ea.Zout = want_z ? Zbuf : nullptr;
         const double mu_next = fmin(mu * p.rho, mubar);                                  // :223
-        ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
         int svp = 0;
-        if (use_w) {
-            // the streaming epilogue is specialised on the rank: fetch svp now (one short extra host sync)
+        if (use_w || fused) {
+            // the streaming / fused kernels are specialised on the rank: fetch svp now (one short extra host sync)
             CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
             if (fast_ok && last_was_fast) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -423,31 +472,85 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                 si_budget = fl[1] ? 12 : fl[3] + 3;
             }
         }
-        {
-            Phase ph(h, TLSQ_PHASE_EPILOGUE);
-            if (fact && !stream_factored_fits(N, svp, svpb[cur])) {
-                // rank estimate beyond the factored kernels: materialise A_{k-1} and continue with the dense iterate
-                CK(alloc_dense_a());
-                CK(launch_fact_to_dense(Tb[cur], Vb[cur], svpb[cur], M, N, nonnegA, Abuf[cur], sms, st, L));
-                ea.Ap = Abuf[cur]; ea.An = Abuf[nxt];
-                fact = false;
-            }
-            if (fact) {
-                ea.Tp = Tb[cur]; ea.Vp = Vb[cur]; ea.svp_prev = svpb[cur]; ea.Tn = Tb[nxt];
-                CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
-                // V_k of this iterate (Vs is overwritten by the next eigen-decomposition)
-                CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
-                svpb[nxt] = svp;
-            } else if (use_w && svp <= kStreamMaxRank) {
-                CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
-            } else {
-                CK(launch_epilogue(ea, hankel, false, sms, st, L));
-            }
+        // will the Frobenius bracket [fro/sqrt(d), fro] probably straddle tol?  (fro shrinks by < 8x per iteration)
+        const bool want_z = (use_w || fused) && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
+        if (fused && (svp > kFusedMaxRank || svpb[cur] > kFusedMaxRank)) {
+            // rank estimate beyond the fused kernel: materialise W_k once and continue on the streaming pipeline
+            CK(ensure_w());
+            EpiArgs wa = {};
+            wa.D = D; wa.Yp = Ybuf[cur]; wa.Tp = Tb[cur]; wa.Vp = Vb[cur]; wa.svp_prev = svpb[cur];
+            wa.Tn = Tb[cur]; wa.Vs = Vb[cur]; wa.M = M; wa.N = N; wa.ldw = M; wa.im = im; wa.eps = eps;
+            wa.nonnegA = nonnegA; wa.nonnegE = nonnegE;
+            CK(launch_final_from_factors(wa, hankel, svpb[cur], Wbuf, sms, st, L));
+            fused = false;
+            use_w = true;
         }
-        CKR(allreduce(h, dscal, 1, kNcclSum));
-        CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
+
+        double zz = 0.0;
+        bool z_gram_ready = false;     // G2 holds Z_k'Z_k (fused path, two-phase iteration)
+        bool y_written = true;
+        EpiArgs ea = {};
+        if (fused) {
+            // ---- one-pass iteration (fused.cu) ----------------------------------------------------------------------
+            FusedArgs f = fa;
+            f.Vp = Vb[cur]; f.svp_prev = svpb[cur]; f.Vs = Vs; f.fvec = fvec; f.svp = svp;
+            f.Yn = Ybuf[nxt]; f.Tn = Tb[nxt];
+            f.im = im; f.eps = eps; f.mu = mu; f.im_next = 1.0 / mu_next; f.eps_next = p.lambda / mu_next;
+            if (want_z) {
+                // phase A of an iteration whose stop test probably needs opnorm(Z): T_k, ||Z||_F^2 and Z'Z; Y is not
+                // touched yet, so that (Y_{k-1}, T_{k-1}, T_k) still describe the solution if this iteration converges
+                Phase ph(h, TLSQ_PHASE_EXACT_COST);
+                f.gram_of = FUSED_GRAM_Z; f.compute_T = 1; f.write_Y = 0;
+                CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], nullptr, G2, G2 + (size_t)n * n, sms, st, L));
+                CKR(allreduce(h, G2, (size_t)n * n + 1, kNcclSum));
+                CK(cudaMemcpyAsync(hp, G2 + (size_t)n * n, 8, cudaMemcpyDeviceToHost, st));
+                z_gram_ready = true;
+                y_written = false;
+            } else {
+                Phase ph(h, TLSQ_PHASE_FUSED);
+                f.gram_of = FUSED_GRAM_WNEXT; f.compute_T = 1; f.write_Y = 1;
+                CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], nullptr, G, G + (size_t)n * n, sms, st, L));
+                CKR(allreduce(h, G, (size_t)n * n + 1, kNcclSum));
+                CK(cudaMemcpyAsync(hp, G + (size_t)n * n, 8, cudaMemcpyDeviceToHost, st));
+                gram_ready = true;
+            }
+            CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
+            svpb[nxt] = svp;
+        } else {
+            // ---- epilogue of the two-kernel pipelines  (:188-192, 205-222) -----------------------------------------
+            CK(cudaMemsetAsync(dscal, 0, 8, st));
+            ea.D = D; ea.Ap = Abuf[cur]; ea.Yp = Ybuf[cur]; ea.An = Abuf[nxt]; ea.Yn = Ybuf[nxt];
+            ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
+            ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
+            ea.zz = dscal;
+            if (want_z && !Zbuf && !inplace_y) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
+            ea.Zout = (want_z && Zbuf) ? Zbuf : nullptr;
+            ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
+            {
+                Phase ph(h, TLSQ_PHASE_EPILOGUE);
+                if (fact && !stream_factored_fits(N, svp, svpb[cur])) {
+                    // rank estimate beyond the factored kernels: materialise A_{k-1} and continue with the dense iterate
+                    CK(alloc_dense_a());
+                    CK(launch_fact_to_dense(Tb[cur], Vb[cur], svpb[cur], M, N, nonnegA, Abuf[cur], sms, st, L));
+                    ea.Ap = Abuf[cur]; ea.An = Abuf[nxt];
+                    fact = false;
+                }
+                if (fact) {
+                    ea.Tp = Tb[cur]; ea.Vp = Vb[cur]; ea.svp_prev = svpb[cur]; ea.Tn = Tb[nxt];
+                    CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
+                    // V_k of this iterate (Vs is overwritten by the next eigen-decomposition)
+                    CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
+                    svpb[nxt] = svp;
+                } else if (use_w && svp <= kStreamMaxRank) {
+                    CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
+                } else {
+                    CK(launch_epilogue(ea, hankel, false, sms, st, L));
+                }
+            }
+            CKR(allreduce(h, dscal, 1, kNcclSum));
+            CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
-        static const bool dbg_eig = getenv("TLSQ_DEBUG_EIG") != nullptr;
         if (dbg_eig) {
             CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
             if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
@@ -460,15 +563,14 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             fprintf(stderr, "[tlsq] iter %lld: full-jacobi sweeps %d | fast: conv %d need_full %d svp %d si_steps %d "
                             "certified %d si_sweeps %d\n", (long long)k, sw, fl[0], fl[1], fl[2], fl[3], fl[4], fl[5]);
         }
-        const double zz = hp[0];
+        zz = hp[0];
         memcpy(&svp, hp + 1, 4);
         svp_last = svp;
         im_last = im; eps_last = eps; prev_idx = cur; last_idx = nxt;
-        mu = mu_next;
         // stop test  cost = opnorm(Z)/d_norm < tol   (:225-231)
         const double fro = sqrt(zz) / d_norm;        // ||Z||_F/d_norm >= cost >= ||Z||_F/(sqrt(d) d_norm)
         double cost_rec = -fro;
-        bool converged;
+        bool converged = false;
         bool need_exact = exact_cost;
         if (!need_exact) {
             if (fro < p.tol) converged = true;
@@ -476,20 +578,37 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             else need_exact = true;
         }
         prev_fro = fro;
+        if (need_exact && inplace_y && !z_gram_ready) {
+            // Y was updated in place and the bracket was not predicted: Z_k cannot be rebuilt.  Only the upper bound
+            // is available -> not converged (at worst one more iteration than the reference).
+            need_exact = false;
+            converged = false;
+        }
         if (need_exact) {
             Phase ph(h, TLSQ_PHASE_EXACT_COST);
-            if (want_z) {
+            if (z_gram_ready) {
+                // G2 = Z'Z came with phase A
+            } else if (fused) {
+                // the bracket was not predicted: Z_k'Z_k from (Y_{k-1}, T_{k-1}, T_k), nothing written
+                FusedArgs f = fa;
+                f.Vp = Vb[cur]; f.svp_prev = svpb[cur]; f.Vs = Vb[nxt]; f.fvec = fvec; f.svp = svp;
+                f.im = im; f.eps = eps; f.mu = mu; f.gram_of = FUSED_GRAM_Z; f.compute_T = 0; f.write_Y = 0;
+                CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], Tb[nxt], G2, nullptr, sms, st, L));
+                CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
+            } else if (want_z && Zbuf) {
                 CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
+                CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             } else if (fact) {
                 // the bracket was not predicted: rebuild Z_k from the factored iterates, then the same SYRK
                 if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
                 CK(launch_z_from_factors(ea, hankel, svp, Zbuf, sms, st, L));
                 CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
+                CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             } else {
                 gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;
                 CK(launch_gram(gs, GRAM_Z, hankel, plan, bPart.as<double>(), G2, st, L));
+                CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             }
-            CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             // bracket lambda_max(Z'Z) by repeated squaring; only a bracket that straddles tol^2 needs the Jacobi
             CK(launch_lmax_bounds(G2, n, sqA, sqB, sqf, sqf + 16, st, L));
             CK(cudaMemcpyAsync(hp, sqf + 16, 16, cudaMemcpyDeviceToHost, st));
@@ -514,6 +633,19 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             o.hist[3 * (k - 1) + 2] = cost_rec;
         }
         k_done = k;
+        if (fused && !y_written && !(converged || k == p.iters)) {
+            // phase B: the iteration goes on -> Y_k and the Gram of W_{k+1}, with T_k taken from phase A
+            Phase ph(h, TLSQ_PHASE_FUSED);
+            FusedArgs f = fa;
+            f.Vp = Vb[cur]; f.svp_prev = svpb[cur]; f.Vs = Vb[nxt]; f.fvec = fvec; f.svp = svp;
+            f.Yn = Ybuf[nxt]; f.Tn = nullptr;
+            f.im = im; f.eps = eps; f.mu = mu; f.im_next = 1.0 / mu_next; f.eps_next = p.lambda / mu_next;
+            f.gram_of = FUSED_GRAM_WNEXT; f.compute_T = 0; f.write_Y = 1;
+            CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], Tb[nxt], G, nullptr, sms, st, L));
+            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+            gram_ready = true;
+        }
+        mu = mu_next;
         cur = nxt;
         if (converged) { conv = 1; break; }
     }
@@ -521,19 +653,33 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // ---- outputs (:238) ----------------------------------------------------------------------------------
     Phase ph_final(h, TLSQ_PHASE_FINALIZE);
     if (fast_ok && last_was_fast && (o.S || o.Vt || o.U)) {
-        // the fast path only carries the dominant block; the returned SVD (:238) needs the full spectrum of the last W
+        // the fast path only carries the dominant block; the returned SVD (:238) needs the full spectrum of the last W.
+        // On the fused path G already holds the Gram of W_{k+1}: rebuild W_k'W_k from (Y_{k-1}, T_{k-1}).
+        if (gram_ready) {
+            FusedArgs f = fa;
+            f.Vp = Vb[prev_idx]; f.svp_prev = svpb[prev_idx]; f.im = im_last; f.eps = eps_last;
+            f.gram_of = FUSED_GRAM_W;
+            CK(launch_alm_fused(f, hankel, Ybuf[prev_idx], Tb[prev_idx], nullptr, G, nullptr, sms, st, L));
+            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+        }
         CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
         CK(launch_svt_post(lam, n, im_last, nukeA, sigma, fvec, dsvp, st, L));
     }
     if (fact) {
         // Factored iterate: ONE pass produces A_k, E_k and (for U) the last SVT input W_k from
         // (T_{k-1}, V_{k-1}, Y_{k-1}) and (T_k, V_k); W_k lands in the W buffer, which is free now.
-        if (o.A || o.E || o.U) {
-            EpiArgs fa = {};
-            fa.D = D; fa.Yp = Ybuf[prev_idx]; fa.Tp = Tb[prev_idx]; fa.Vp = Vb[prev_idx]; fa.svp_prev = svpb[prev_idx];
-            fa.Tn = Tb[last_idx]; fa.Vs = Vb[last_idx]; fa.An = o.A; fa.Eout = o.E; fa.M = M; fa.N = N; fa.ldw = M;
-            fa.im = im_last; fa.eps = eps_last; fa.nonnegA = nonnegA; fa.nonnegE = nonnegE;
-            CK(launch_final_from_factors(fa, hankel, svpb[last_idx], o.U ? Wbuf : nullptr, sms, st, L));
+        if (o.uh_sum)
+            CK(launch_unhankel_factors(Tb[last_idx], M, Vb[last_idx], svpb[last_idx], nonnegA, o.uh_r0, M, N, o.uh_Ns,
+                                       o.uh_sum, sms, st, L));
+        if (o.U) CK(ensure_w());
+        if (o.E || o.U) {
+            EpiArgs fe = {};
+            fe.D = D; fe.Yp = Ybuf[prev_idx]; fe.Tp = Tb[prev_idx]; fe.Vp = Vb[prev_idx]; fe.svp_prev = svpb[prev_idx];
+            fe.Tn = Tb[last_idx]; fe.Vs = Vb[last_idx]; fe.An = o.A; fe.Eout = o.E; fe.M = M; fe.N = N; fe.ldw = M;
+            fe.im = im_last; fe.eps = eps_last; fe.nonnegA = nonnegA; fe.nonnegE = nonnegE;
+            CK(launch_final_from_factors(fe, hankel, svpb[last_idx], o.U ? Wbuf : nullptr, sms, st, L));
+        } else if (o.A) {
+            CK(launch_fact_to_dense(Tb[last_idx], Vb[last_idx], svpb[last_idx], M, N, nonnegA, o.A, sms, st, L));
         }
         if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
         if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
@@ -551,14 +697,21 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                 for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
                 CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
                 CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
-                EpiArgs ea = {};
-                ea.D = D; ea.Ap = Zbuf; ea.Yp = Ybuf[prev_idx]; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M;
-                ea.Vs = Vs; ea.fvec = fvec; ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last;
-                ea.nonnegA = nonnegA; ea.nonnegE = nonnegE; ea.zz = dscal;
-                CK(launch_epilogue(ea, hankel, true, sms, st, L));
+                EpiArgs eu = {};
+                eu.D = D; eu.Ap = Zbuf; eu.Yp = Ybuf[prev_idx]; eu.Uout = o.U; eu.M = M; eu.N = N; eu.ldw = M;
+                eu.Vs = Vs; eu.fvec = fvec; eu.svp = dsvp; eu.im = im_last; eu.eps = eps_last;
+                eu.nonnegA = nonnegA; eu.nonnegE = nonnegE; eu.zz = dscal;
+                CK(launch_epilogue(eu, hankel, true, sms, st, L));
             }
         }
     } else {
+    if (o.uh_sum) {
+        // the rank estimate left the factored path: anti-diagonal sums from the dense A_k
+        DevBuf bCnt;
+        CK(bCnt.alloc((size_t)o.uh_Ns * 8, st));
+        CK(cudaMemsetAsync(o.uh_sum, 0, (size_t)o.uh_Ns * 8, st));
+        CK(launch_unhankel_partial(Abuf[last_idx], o.uh_r0, M, N, 1, o.uh_Ns, o.uh_sum, bCnt.as<double>(), st, L));
+    }
     // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
     // produced before A_k is copied there.
     const double* Aprev_dense = Abuf[prev_idx];
@@ -575,13 +728,13 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
         CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
-        EpiArgs ea = {};
-        ea.D = D; ea.Ap = Aprev_dense; ea.Yp = Ybuf[prev_idx]; ea.An = nullptr; ea.Yn = nullptr;
-        ea.Wn = nullptr; ea.im_next = 0.0; ea.eps_next = 0.0; ea.Zout = nullptr;
-        ea.Eout = nullptr; ea.Uout = o.U; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
-        ea.svp = dsvp; ea.im = im_last; ea.eps = eps_last; ea.mu = 0.0; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
-        ea.zz = dscal;
-        CK(launch_epilogue(ea, hankel, true, sms, st, L));
+        EpiArgs eu = {};
+        eu.D = D; eu.Ap = Aprev_dense; eu.Yp = Ybuf[prev_idx]; eu.An = nullptr; eu.Yn = nullptr;
+        eu.Wn = nullptr; eu.im_next = 0.0; eu.eps_next = 0.0; eu.Zout = nullptr;
+        eu.Eout = nullptr; eu.Uout = o.U; eu.M = M; eu.N = N; eu.ldw = M; eu.Vs = Vs; eu.fvec = fvec;
+        eu.svp = dsvp; eu.im = im_last; eu.eps = eps_last; eu.mu = 0.0; eu.nonnegA = nonnegA; eu.nonnegE = nonnegE;
+        eu.zz = dscal;
+        CK(launch_epilogue(eu, hankel, true, sms, st, L));
     }
     if (o.A && Abuf[last_idx] != o.A)
         CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
@@ -719,6 +872,29 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
     const int64_t K = (Ns - n) / lag + 1;                                                // :81
     if (!(p.lambda > 0.0)) p.lambda = 1.0 / sqrt((double)(K > n ? K : n));               // :157
     cudaStream_t st = h->stream;
+    // Factored unhankel (lag 1, tall enough for the factored iterate): A is never materialised -- the anti-diagonal
+    // sums are taken straight from A_k = clamp(T_k V_k'); sharded runs all-reduce the Ns partial sums.
+    {
+        static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
+        const int64_t base = K / h->nranks, rem = K % h->nranks;
+        const int64_t r0 = h->rank * base + (h->rank < rem ? h->rank : rem);
+        const int64_t Kl = base + (h->rank < rem ? 1 : 0);
+        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && Kl >= 1 &&
+            syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), Kl, n, Kl)) {
+            CKR(check_rpca_args(Kl, n, p));
+            DevBuf bSum;
+            CK(bSum.alloc((size_t)Ns * 8, st));
+            RpcaOut ol;
+            ol.sv = sv; ol.iters_done = iters_done; ol.converged = converged; ol.hist = hist;
+            ol.uh_sum = bSum.as<double>(); ol.uh_r0 = r0; ol.uh_Ns = Ns;
+            MatSrc srcl{y + r0, 1};
+            CKR(rpca_core(h, srcl, true, Kl, n, p, ol));
+            CKR(allreduce(h, ol.uh_sum, (size_t)Ns, kNcclSum));
+            CK(launch_unhankel_divide_count(ol.uh_sum, K, n, Ns, yf, st, &h->launches));
+            CK(cudaStreamSynchronize(st));
+            return TLSQ_OK;
+        }
+    }
     if (h->nranks > 1) {
         // Row-sharded: every rank holds the (small) full signal and works on Hankel rows [r0, r1) through the same
         // implicit index functor; only the n x n Gram, scalars and the anti-diagonal sums are all-reduced.
