@@ -28,6 +28,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram read+write per launch of alm_fused_kernel from `ncu --set full` (profiles/), keyed by (rows per GPU, columns)
+FUSED_TRAFFIC_GB = {}
+
 FP64_TENSOR_PEAK_TFLOPS = 37.1      # measured on this pool's B200 (tools/microbench.cu -> profiles/r01_microbench_fp64_hbm.log)
 
 WORKLOADS = {
@@ -309,27 +312,45 @@ def run_b200(args, w, rank, world, local_rank):
         g_ms, g_n = prof["gram"]
         e_ms, e_n = prof["epilogue"]
         j_ms, j_n = prof["eig"]
-        gram_flops = m * N * (N + 1)                               # SYRK count per launch (SURVEY.md 8d)
-        t_gram = g_ms / max(g_n, 1) * 1e-3
-        ach = gram_flops / t_gram * 1e-12 if t_gram > 0 else 0.0
-        line["roofline"] = {"kernel": "gram_kernel<GRAM_W> (DMMA SYRK of the SVT input)", "bound": "tensor",
-                            "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                            "frac": ach / FP64_TENSOR_PEAK_TFLOPS,
-                            "peak_source": "measured FP64 DMMA peak, profiles/r01_microbench_fp64_hbm.log "
-                                           "(MEASURED_PEAKS.json has no FP64 figure)",
-                            "traffic": None, "avg_launch_ms": t_gram * 1e3}
-        S = m * N * 8
-        t_epi = e_ms / max(e_n, 1) * 1e-3
-        line["roofline_epilogue"] = {"kernel": "epilogue_kernel", "bound": "hbm",
-                                     "achieved": 6 * S / t_epi * 1e-9 if t_epi > 0 else 0.0, "peak": hbm,
-                                     "unit": "GB/s", "frac": (6 * S / t_epi * 1e-9) / hbm if t_epi > 0 else 0.0,
-                                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
-                                     "algorithmic_bytes": "6*S (reads D,A,Y; writes A,E,Y; SURVEY.md 8d)",
-                                     "avg_launch_ms": t_epi * 1e3}
-        # per-iteration roofline (SURVEY.md 8d):  max(F_gram/P64, 3S/BW) + max(F_epi/P64, 6S/BW)
+        f_ms, f_n = prof.get("fused", (0.0, 0))
         svp = w["rank"]
+        S = m * N * 8
+        gram_flops = m * N * (N + 1)                               # SYRK count per launch (SURVEY.md 8d)
+        epi_flops = 4 * m * N * svp + 12 * m * N                   # low-rank reconstruction + element-wise (8d)
+        peak_src64 = ("measured FP64 DMMA peak, profiles/r01_microbench_fp64_hbm.log "
+                      "(MEASURED_PEAKS.json has no FP64 figure)")
+        if f_n > 0:
+            # one-pass pipeline: the dominant kernel is alm_fused_kernel (epilogue of iteration k + Gram of iteration
+            # k+1).  Both halves run on the FP64 pipe (DMMA and DFMA share it), so the bound is FP64 arithmetic.
+            t_f = f_ms / f_n * 1e-3
+            ach = (gram_flops + epi_flops) / t_f * 1e-12
+            line["roofline"] = {"kernel": "alm_fused_kernel (epilogue of iteration k + DMMA Gram of iteration k+1, "
+                                          "one HBM pass)", "bound": "tensor", "achieved": ach,
+                                "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_TENSOR_PEAK_TFLOPS,
+                                "peak_source": peak_src64, "algorithmic_flops": "M*N*(N+1) + 4*M*N*svp + 12*M*N "
+                                "(SURVEY.md 8d: F_gram + F_epi)", "traffic": FUSED_TRAFFIC_GB.get((m, N)),
+                                "traffic_unit": "GB per launch (dram read+write, ncu --set full, profiles/)",
+                                "avg_launch_ms": t_f * 1e3, "launches_profiled": f_n,
+                                "hbm_view": {"algorithmic_GBps": 9 * S / t_f * 1e-9, "moved_GBps": 3 * S / t_f * 1e-9,
+                                             "peak": hbm, "note": "9S = SURVEY 8d two-pass count; the kernel moves 3S "
+                                                                   "(reads D, Y; writes Y)"}}
+        else:
+            t_gram = g_ms / max(g_n, 1) * 1e-3
+            ach = gram_flops / t_gram * 1e-12 if t_gram > 0 else 0.0
+            line["roofline"] = {"kernel": "syrk_tma_kernel (DMMA SYRK of the SVT input)", "bound": "tensor",
+                                "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                "frac": ach / FP64_TENSOR_PEAK_TFLOPS, "peak_source": peak_src64,
+                                "traffic": None, "avg_launch_ms": t_gram * 1e3}
+            t_epi = e_ms / max(e_n, 1) * 1e-3
+            line["roofline_epilogue"] = {"kernel": "alm_stream_kernel", "bound": "hbm",
+                                         "achieved": 6 * S / t_epi * 1e-9 if t_epi > 0 else 0.0, "peak": hbm,
+                                         "unit": "GB/s", "frac": (6 * S / t_epi * 1e-9) / hbm if t_epi > 0 else 0.0,
+                                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                                         "algorithmic_bytes": "6*S (reads D,A,Y; writes A,E,Y; SURVEY.md 8d)",
+                                         "avg_launch_ms": t_epi * 1e3}
+        # per-iteration roofline (SURVEY.md 8d):  max(F_gram/P64, 3S/BW) + max(F_epi/P64, 6S/BW)
         t_roof = max(gram_flops / (FP64_TENSOR_PEAK_TFLOPS * 1e12), 3 * S / (hbm * 1e9)) + \
-            max((4 * m * N * svp + 12 * m * N) / (FP64_TENSOR_PEAK_TFLOPS * 1e12), 6 * S / (hbm * 1e9))
+            max(epi_flops / (FP64_TENSOR_PEAK_TFLOPS * 1e12), 6 * S / (hbm * 1e9))
         t_iter = ms * 1e-3 / max(iters_total, 1)
         line["iteration_roofline"] = {"roofline_ms": t_roof * 1e3, "measured_ms": t_iter * 1e3,
                                       "frac": t_roof / t_iter if t_iter > 0 else 0.0,

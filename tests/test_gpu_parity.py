@@ -86,7 +86,11 @@ def test_golden_vectors():
     (3000, 40, 3, {"nonnegA": True}, 12),
     (496, 5, 2, {}, 20),                                     # README shape (C1)
     (5001, 200, 5, {"nukeA": False}, 9),                     # odd leading dimension: no TMA, generic Gram
-    (8192, 256, 10, {}, 14),                                 # TMA SYRK + fast eigen path + streaming epilogue
+    (8192, 256, 10, {}, 14),                                 # n = 256: fused one-pass kernel + fast eigen path
+    (20002, 256, 10, {"nonnegA": True, "nonnegE": True}, 12),  # fused, row count not a multiple of the 32-row tile
+    (6000, 256, 3, {"nukeA": False}, 8),                     # fused, nukeA = false
+    (8000, 256, 20, {}, 12),                                 # fused until svp > 16, then the streaming pipeline
+    (8192, 192, 10, {}, 14),                                 # TMA SYRK + fast eigen path + streaming epilogue
     (10000, 128, 6, {"nonnegA": True, "nonnegE": True}, 14),
     (3000, 96, 40, {}, 10),                                  # svp > 32: fused tile epilogue, full Jacobi
     (6000, 512, 8, {}, 5),                                   # n = 512: cooperative-grid Jacobi
@@ -188,6 +192,29 @@ def test_lowrankfilter_parity_and_statistics():
     assert relF(yf, O.unhankel_fast(A)) < TOL
     # lag > 1
     assert relF(T.lowrankfilter(yn[:600], 30, lag=3), O.lowrankfilter(yn[:600], 30, lag=3)) < TOL
+
+
+def test_fused_pipeline_equals_two_kernel_pipeline(monkeypatch):
+    """n = 256: the one-pass cluster kernel (fused.cu) against the streaming epilogue + SYRK pipeline it replaces, and
+    the implicit-Hankel / in-place-Y / factored-unhankel variants of lowrankfilter against the oracle."""
+    D = T.synth.lowrank_sparse_np(16384, 256, 7, 0.05, seed=9)
+    A1, E1, s1, sv1, i1 = T.rpca(D, return_info=True)
+    monkeypatch.setenv("TLSQ_NO_FUSED", "1")
+    A2, E2, s2, sv2, i2 = T.rpca(D, return_info=True)
+    monkeypatch.delenv("TLSQ_NO_FUSED")
+    assert i1["iters"] == i2["iters"] and sv1 == sv2
+    assert relF(A1, A2) < 1e-12 and relF(E1, E2) < 1e-12 and np.array_equal(E1 != 0, E2 != 0)
+    assert np.allclose(s1.S, s2.S, rtol=0, atol=1e-12 * s2.S[0])
+    y, yn = T.synth.sinusoid_np(12255, seed=2, noise=0.05)                # K = 12000 Hankel rows x 256
+    yo = O.lowrankfilter(yn, 256)
+    yf, info = T.lowrankfilter(yn, 256, return_info=True)
+    assert relF(yf, yo) < TOL
+    monkeypatch.setenv("TLSQ_INPLACE_Y", "1")                             # dual variable updated in place
+    yf2, info2 = T.lowrankfilter(yn, 256, return_info=True)
+    monkeypatch.delenv("TLSQ_INPLACE_Y")
+    assert relF(yf2, yo) < TOL and info2["iters"] == info["iters"]
+    yf3 = T.lowrankfilter(yn[:-1], 256)                                   # odd row count: two-kernel pipeline
+    assert relF(yf3, O.lowrankfilter(yn[:-1], 256)) < TOL
 
 
 @pytest.mark.parametrize("d,N,r", [(10, 40, 3), (40, 10, 5), (1000, 256, 4), (5000, 300, 3), (777, 1000, 2)])

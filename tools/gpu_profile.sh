@@ -11,6 +11,6 @@ cat gpurun_out/bench_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_launch_$TAG.log 2>&1
 # full captures of the two dominant kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'syrk_tma_kernel|alm_stream_kernel' -s 12 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'syrk_tma_kernel|alm_stream_kernel|alm_fused_kernel' -s 12 -c 4 \
     -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out | tail -8

@@ -74,25 +74,39 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
+// sum_c t[c] v[c] with four independent FMA chains (RP is a multiple of 4; v is 16-byte aligned shared memory)
 template <int RP>
 __device__ __forceinline__ double dot_rp(const double (&t)[RP], const double* __restrict__ v) {
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-    for (int c = 0; c < RP; c += 2) {
-        const double2 vv = *reinterpret_cast<const double2*>(v + c);
-        acc = fma(t[c], vv.x, acc);
-        acc = fma(t[c + 1], vv.y, acc);
+    for (int c = 0; c < RP; c += 4) {
+        const double2 v0 = *reinterpret_cast<const double2*>(v + c);
+        const double2 v1 = *reinterpret_cast<const double2*>(v + c + 2);
+        a0 = fma(t[c], v0.x, a0);
+        a1 = fma(t[c + 1], v0.y, a1);
+        a2 = fma(t[c + 2], v1.x, a2);
+        a3 = fma(t[c + 3], v1.y, a3);
     }
-    return acc;
+    return (a0 + a1) + (a2 + a3);
 }
+
+// TMA store of a shared-memory tile (bulk async group); the generic-proxy writes must be fenced by their writers
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(x), "r"(y), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // One 32-row tile of the Gram: the first N1 strips of the warp take their A fragments from tile row A, the others
 // from tile row B (N1 is a per-warp constant; the switch at the call site keeps the accumulator indexing static).
 template <int N1>
 __device__ __forceinline__ void gram_phase(double (&acc)[9][4][2], const double* __restrict__ W2s, int aoffA, int aoffB,
-                                           const int (&boff)[9]) {
+                                           const int (&boff)[9], int ks0, int ks1) {
 #pragma unroll 1
-    for (int ks = 0; ks < FR / 4; ++ks) {
+    for (int ks = ks0; ks < ks1; ++ks) {
         const double* wk = W2s + 4 * ks;
         double a1[4], a2[4];
 #pragma unroll
@@ -120,7 +134,7 @@ template <int RP, bool HANKEL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__ CUtensorMap mY,
                  const __grid_constant__ CUtensorMap mTp, const __grid_constant__ CUtensorMap mTn,
-                 const FusedDev p) {
+                 const __grid_constant__ CUtensorMap mYo, const __grid_constant__ CUtensorMap mTo, const FusedDev p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     double* W2s = reinterpret_cast<double*>(smem);              // [256][36] DMMA operand tile (both halves)
     double* Ds = reinterpret_cast<double*>(smem + W2_BYTES);    // [128][32] own-half D tile          (TMA)
@@ -129,7 +143,7 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
     double* Vps = Es + TILE_DOUBLES;                            // [128][RP] own-half rows of V_{k-1}
     double* Vks = Vps + FH * RP;                                // [128][RP] own-half rows of V_k
     double* Tps = Vks + FH * RP;                                // [RP][32]  T_{k-1} tile             (TMA)
-    double* Tns = Tps + RP * FR;                                // [RP][32]  T_k tile when it is given (TMA)
+    double* Tns = Tps + RP * FR;                                // [RP][32]  T_k tile: TMA load when given, else TMA-store staging
     double* Tsum = Tns + RP * FR;                               // [2][RP][32] partial row sums of the two CTAs
     double* fs = Tsum + 2 * RP * FR;                            // [RP] shrink factors
     double* red = fs + RP;                                      // [8]
@@ -144,6 +158,8 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
     const int c0 = (int)rank * FH;
     const int go = a.gram_of;
     const bool simple = (go == FUSED_GRAM_W) || (go == FUSED_GRAM_D);
+    const bool nnA = a.nonnegA != 0;
+    constexpr int UB = 8;
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -213,6 +229,8 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
                 Es[jl * FR + lane] = d;
             }
         } else {
+            // staged in batches of UB elements so that every stage exposes UB independent dependency chains (the
+            // FP64 pipe is shared by only two warps per scheduler: instruction-level parallelism must hide its latency)
             double tp[RP], tr[RP];
 #pragma unroll
             for (int c = 0; c < RP; ++c) {
@@ -220,22 +238,31 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
                 tr[c] = 0.0;
             }
 #pragma unroll 1
-            for (int u = 0; u < 16; ++u) {
-                const int jl = 16 * warp + u;
-                const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
-                const double yp = Ys[jl * FR + lane];
-                double ap = dot_rp<RP>(tp, Vps + jl * RP);
-                if (a.nonnegA) ap = (__double_as_longlong(ap) > 0) ? ap : 0.0;
-                double e, w;
-                alm_ew(d, ap, yp, a.im, a.eps, a.nonnegE, e, w);
-                Es[jl * FR + lane] = (go == FUSED_GRAM_W) ? w : e;
-                if (a.compute_T) {
-                    const double* v = Vks + jl * RP;
+            for (int u0 = 0; u0 < 16; u0 += UB) {
+                double av[UB], wv[UB];
 #pragma unroll
-                    for (int c = 0; c < RP; c += 2) {
-                        const double2 vv = *reinterpret_cast<const double2*>(v + c);
-                        tr[c] = fma(w, vv.x, tr[c]);
-                        tr[c + 1] = fma(w, vv.y, tr[c + 1]);
+                for (int u = 0; u < UB; ++u) av[u] = dot_rp<RP>(tp, Vps + (16 * warp + u0 + u) * RP);
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int jl = 16 * warp + u0 + u;
+                    const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
+                    const double yp = Ys[jl * FR + lane];
+                    const double ap = (nnA && !(__double_as_longlong(av[u]) > 0)) ? 0.0 : av[u];
+                    double e, w;
+                    alm_ew(d, ap, yp, a.im, a.eps, a.nonnegE, e, w);
+                    Es[jl * FR + lane] = (go == FUSED_GRAM_W) ? w : e;
+                    wv[u] = w;
+                }
+                if (a.compute_T) {
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const double* v = Vks + (16 * warp + u0 + u) * RP;
+#pragma unroll
+                        for (int c = 0; c < RP; c += 2) {
+                            const double2 vv = *reinterpret_cast<const double2*>(v + c);
+                            tr[c] = fma(wv[u], vv.x, tr[c]);
+                            tr[c + 1] = fma(wv[u], vv.y, tr[c + 1]);
+                        }
                     }
                 }
             }
@@ -271,50 +298,64 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < RP; ++c) {
                     tk[c] = fs[c] * (Tsum[c * FR + lane] + Tsum[(RP + c) * FR + lane]);
-                    if (rank == 0 && (c & 7) == warp && rowok && a.Tn) a.Tn[(int64_t)c * a.ldt + row] = tk[c];
+                    if (rank == 0 && (c & 7) == warp) Tns[c * FR + lane] = tk[c];          // staged for the TMA store
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < RP; ++c) tk[c] = c < a.svp ? Tns[c * FR + lane] : 0.0;
             }
 #pragma unroll 1
-            for (int u = 0; u < 16; ++u) {
-                const int jl = 16 * warp + u;
-                const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
-                const double yp = Ys[jl * FR + lane];
-                const double e = Es[jl * FR + lane];
-                double an = dot_rp<RP>(tk, Vks + jl * RP);
-                if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;         // A .= max.(A, 0)   :218
-                const double z = __dsub_rn(__dsub_rn(d, an), e);                        // @. Z = D - A - E  :221
-                const double yn = __dadd_rn(yp, __dmul_rn(a.mu, z));                    // @. Y = Y + mu*Z   :222
-                zz = fma(z, z, zz);
-                if (a.write_Y && rowok) a.Yn[(int64_t)(c0 + jl) * a.ldy + row] = yn;
-                double val = z;
-                if (go == FUSED_GRAM_WNEXT) {
+            for (int u0 = 0; u0 < 16; u0 += UB) {
+                double av[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) av[u] = dot_rp<RP>(tk, Vks + (16 * warp + u0 + u) * RP);
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int jl = 16 * warp + u0 + u;
+                    const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
+                    const double yp = Ys[jl * FR + lane];
+                    const double e = Es[jl * FR + lane];
+                    const double an = (nnA && !(__double_as_longlong(av[u]) > 0)) ? 0.0 : av[u];   // max.(A, 0) :218
+                    const double z = __dsub_rn(__dsub_rn(d, an), e);                    // @. Z = D - A - E  :221
+                    const double yn = __dadd_rn(yp, __dmul_rn(a.mu, z));                // @. Y = Y + mu*Z   :222
+                    zz = fma(z, z, zz);
+                    Es[jl * FR + lane] = yn;                                            // staged for the TMA store
                     double e2, w2;
                     alm_ew(d, an, yn, a.im_next, a.eps_next, a.nonnegE, e2, w2);        // SVT input of iteration k+1
-                    val = w2;
+                    const double val = (go == FUSED_GRAM_WNEXT) ? w2 : z;
+                    const int off = (c0 + jl) * FWS + lane;
+                    W2s[off] = val;
+                    if (push) st_cluster(w2_peer + (uint32_t)off * 8u, val);
                 }
-                const int off = (c0 + jl) * FWS + lane;
-                W2s[off] = val;
-                if (push) st_cluster(w2_peer + (uint32_t)off * 8u, val);
             }
         }
+        if (!simple) fence_async_smem();        // Y_k / T_k tiles were written through the generic proxy
         cluster_arrive();                                                              // C2
         cluster_wait();
-        if (tid == 0 && tile + p.ncluster < p.ntiles) issue(tile + p.ncluster);        // staging is free again
+        if (tid == 0 && !simple) {
+            if (a.write_Y) tma_store_2d(&mYo, tile * FR, c0, Es);
+            if (a.compute_T && rank == 0 && a.Tn) tma_store_2d(&mTo, tile * FR, 0, Tns);
+            tma_commit();
+        }
+        if (tid == 0 && tile + p.ncluster < p.ntiles) issue(tile + p.ncluster);        // D / Y / T staging is free again
 
-        // ---- DMMA phase: G += W2' W2 over this warp's 9 strips ---------------------------------------------------
-        switch (n1) {
-            case 1: gram_phase<1>(acc, W2s, aoffA, aoffB, boff); break;
-            case 2: gram_phase<2>(acc, W2s, aoffA, aoffB, boff); break;
-            case 3: gram_phase<3>(acc, W2s, aoffA, aoffB, boff); break;
-            case 4: gram_phase<4>(acc, W2s, aoffA, aoffB, boff); break;
-            case 5: gram_phase<5>(acc, W2s, aoffA, aoffB, boff); break;
-            case 6: gram_phase<6>(acc, W2s, aoffA, aoffB, boff); break;
-            case 7: gram_phase<7>(acc, W2s, aoffA, aoffB, boff); break;
-            case 8: gram_phase<8>(acc, W2s, aoffA, aoffB, boff); break;
-            default: gram_phase<9>(acc, W2s, aoffA, aoffB, boff); break;
+        // ---- DMMA phase: G += W2' W2 over this warp's 9 strips; the next tile's loads are issued half-way, when the
+        //      TMA stores above have long finished reading their staging buffers -------------------------------------
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int ks0 = half * (FR / 8), ks1 = ks0 + FR / 8;
+            switch (n1) {
+                case 1: gram_phase<1>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 2: gram_phase<2>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 3: gram_phase<3>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 4: gram_phase<4>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 5: gram_phase<5>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 6: gram_phase<6>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 7: gram_phase<7>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                case 8: gram_phase<8>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+                default: gram_phase<9>(acc, W2s, aoffA, aoffB, boff, ks0, ks1); break;
+            }
+            if (half == 0 && tid == 0) tma_wait_read0();     // the stores have read Es / Tns long ago: no stall; S3 publishes it
         }
         __syncthreads();                                                               // S3: operand tile is free
     }
@@ -344,6 +385,7 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
         for (int w8 = 0; w8 < 8; ++w8) s += red[w8];
         a.zpart[blockIdx.x] = s;
     }
+    if (tid == 0) tma_wait_all0();
     cluster_arrive();            // keep this CTA's shared memory alive until the peer is done with it
     cluster_wait();
 }
@@ -429,7 +471,7 @@ struct Inst {
 
 template <int RP, bool HANKEL>
 cudaError_t launch_inst(const CUtensorMap& mD, const CUtensorMap& mY, const CUtensorMap& mTp, const CUtensorMap& mTn,
-                        FusedDev p, int sm_count, cudaStream_t st, int* ncluster_out) {
+                        const CUtensorMap& mYo, const CUtensorMap& mTo, FusedDev p, int sm_count, cudaStream_t st, int* ncluster_out) {
     static Inst inst;
     auto kern = alm_fused_kernel<RP, HANKEL>;
     const size_t smem = smem_bytes<RP>();
@@ -455,15 +497,14 @@ cudaError_t launch_inst(const CUtensorMap& mD, const CUtensorMap& mY, const CUte
     if (nc > p.ntiles) nc = p.ntiles > 0 ? p.ntiles : 1;
     p.ncluster = nc;
     *ncluster_out = nc;
-    kern<<<2 * nc, 256, smem, st>>>(mD, mY, mTp, mTn, p);
+    kern<<<2 * nc, 256, smem, st>>>(mD, mY, mTp, mTn, mYo, mTo, p);
     return cudaGetLastError();
 }
 
 template <int RP>
-cudaError_t launch_rp(bool hankel, const CUtensorMap& mD, const CUtensorMap& mY, const CUtensorMap& mTp,
-                      const CUtensorMap& mTn, const FusedDev& p, int sm_count, cudaStream_t st, int* nc) {
-    return hankel ? launch_inst<RP, true>(mD, mY, mTp, mTn, p, sm_count, st, nc)
-                  : launch_inst<RP, false>(mD, mY, mTp, mTn, p, sm_count, st, nc);
+cudaError_t launch_rp(bool hankel, const CUtensorMap* m, const FusedDev& p, int sm_count, cudaStream_t st, int* nc) {
+    return hankel ? launch_inst<RP, true>(m[0], m[1], m[2], m[3], m[4], m[5], p, sm_count, st, nc)
+                  : launch_inst<RP, false>(m[0], m[1], m[2], m[3], m[4], m[5], p, sm_count, st, nc);
 }
 
 }  // namespace
@@ -502,20 +543,25 @@ cudaError_t launch_alm_fused(const FusedArgs& a, bool hankel, const double* Yp, 
     if (p.has_y && !Yp) return cudaErrorInvalidValue;
     // a valid (even if unused) tensor map for every slot
     const double* any = a.partial;      // cudaMalloc-aligned placeholder for the unused slots
-    CUtensorMap mD, mY, mTp, mTn;
+    CUtensorMap m[6];      // D, Y_{k-1}, T_{k-1}, T_k (given), Y_k out, T_k out
     bool ok = true;
-    ok &= hankel ? encode_map(&mD, any, 32, 128, 32, FR, FH) : encode_map(&mD, a.D.p, a.M, FN, a.D.ld, FR, FH);
-    ok &= p.has_y ? encode_map(&mY, Yp, a.M, FN, a.ldy, FR, FH) : encode_map(&mY, any, 32, 128, 32, FR, FH);
-    ok &= p.has_tp ? encode_map(&mTp, Tp, a.M, kStreamMaxRank, a.ldt, FR, rp) : encode_map(&mTp, any, 32, 128, 32, FR, rp);
-    ok &= p.has_tn ? encode_map(&mTn, Tn_given, a.M, kStreamMaxRank, a.ldt, FR, rp) : encode_map(&mTn, any, 32, 128, 32, FR, rp);
+    ok &= hankel ? encode_map(&m[0], any, 32, 128, 32, FR, FH) : encode_map(&m[0], a.D.p, a.M, FN, a.D.ld, FR, FH);
+    ok &= p.has_y ? encode_map(&m[1], Yp, a.M, FN, a.ldy, FR, FH) : encode_map(&m[1], any, 32, 128, 32, FR, FH);
+    ok &= p.has_tp ? encode_map(&m[2], Tp, a.M, kStreamMaxRank, a.ldt, FR, rp) : encode_map(&m[2], any, 32, 128, 32, FR, rp);
+    ok &= p.has_tn ? encode_map(&m[3], Tn_given, a.M, kStreamMaxRank, a.ldt, FR, rp) : encode_map(&m[3], any, 32, 128, 32, FR, rp);
+    const bool y_out = needs_tk && a.write_Y && a.Yn;
+    const bool t_out = needs_tk && a.compute_T && a.Tn;
+    ok &= y_out ? encode_map(&m[4], a.Yn, a.M, FN, a.ldy, FR, FH) : encode_map(&m[4], any, 32, 128, 32, FR, FH);
+    ok &= t_out ? encode_map(&m[5], a.Tn, a.M, kStreamMaxRank, a.ldt, FR, rp) : encode_map(&m[5], any, 32, 128, 32, FR, rp);
     if (!ok) return cudaErrorInvalidValue;
+    if (needs_tk && a.write_Y && !a.Yn) return cudaErrorInvalidValue;
     int nc = 0;
     cudaError_t e;
     switch (rp) {
-        case 4:  e = launch_rp<4>(hankel, mD, mY, mTp, mTn, p, sm_count, st, &nc); break;
-        case 8:  e = launch_rp<8>(hankel, mD, mY, mTp, mTn, p, sm_count, st, &nc); break;
-        case 12: e = launch_rp<12>(hankel, mD, mY, mTp, mTn, p, sm_count, st, &nc); break;
-        default: e = launch_rp<16>(hankel, mD, mY, mTp, mTn, p, sm_count, st, &nc); break;
+        case 4:  e = launch_rp<4>(hankel, m, p, sm_count, st, &nc); break;
+        case 8:  e = launch_rp<8>(hankel, m, p, sm_count, st, &nc); break;
+        case 12: e = launch_rp<12>(hankel, m, p, sm_count, st, &nc); break;
+        default: e = launch_rp<16>(hankel, m, p, sm_count, st, &nc); break;
     }
     if (e != cudaSuccess) return e;
     fused_reduce_kernel<<<(FN * FN + 255) / 256, 256, 0, st>>>(a.partial, nc, a.zpart, 2 * nc, G, zz_out);
