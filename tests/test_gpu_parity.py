@@ -97,34 +97,51 @@ def test_golden_vectors():
     (300, 500, 4, {}, 8),                                    # wide: solved on the transpose
     (33, 7, 2, {}, 6), (1, 5, 1, {}, 3), (7, 1, 1, {}, 3),   # ragged / degenerate
 ])
-def test_rpca_parity_fixed_iterations(M, N, r, kw, its):
+def test_rpca_parity_fixed_iterations(M, N, r, kw, its, monkeypatch):
     D = T.synth.lowrank_sparse_np(M, N, r, 0.05, seed=M + N, nonneg=bool(kw.get("nonnegA")))
-    A, E, s, sv, info, ref = fixed_iters(D, its, **kw)
-    assert relF(A, ref.A) < TOL, relF(A, ref.A)
-    assert relF(E, ref.E) < TOL or np.linalg.norm(ref.E) == 0
-    assert support_mismatch(E, ref.E, np.abs(D).max()) == 0
-    assert np.array_equal(info["hist"][:, 1], ref.hist[:, 1])          # identical rank history (full-SVD semantics)
-    assert sv == ref.sv
-    d = min(M, N)
-    assert s.U.shape == (M, d) and s.S.shape == (d,) and s.Vt.shape == (d, N)
-    assert np.allclose(s.S, ref.s.S, rtol=0, atol=1e-9 * ref.s.S[0])
-    # the returned SVD reproduces the last SVT input like the reference's does
-    Wg, Wo = (s.U * s.S) @ s.Vt, (ref.s.U * ref.s.S) @ ref.s.Vt
-    assert relF(Wg, Wo) < 1e-7
+    # n = 256 has three interchangeable per-iteration pipelines (solver.cu picks by memory): cover all of them
+    pipelines = [{}]
+    if N == 256 and M >= 4096:
+        pipelines = [{"TLSQ_FUSED": "0"}, {"TLSQ_FUSED": "1"}, {"TLSQ_FUSED": "1", "TLSQ_FUSED_WS": "1"}]
+    ref = None
+    for env in pipelines:
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            A, E, s, sv, info = T.rpca(D, iters=its, tol=0.0, return_info=True, **kw)
+            if ref is None:
+                ref = O.rpca(D, iters=its, tol=0.0, **kw)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        assert relF(A, ref.A) < TOL, (env, relF(A, ref.A))
+        assert relF(E, ref.E) < TOL or np.linalg.norm(ref.E) == 0
+        assert support_mismatch(E, ref.E, np.abs(D).max()) == 0
+        assert np.array_equal(info["hist"][:, 1], ref.hist[:, 1])      # identical rank history (full-SVD semantics)
+        assert sv == ref.sv
+        d = min(M, N)
+        assert s.U.shape == (M, d) and s.S.shape == (d,) and s.Vt.shape == (d, N)
+        assert np.allclose(s.S, ref.s.S, rtol=0, atol=1e-9 * ref.s.S[0])
+        # the returned SVD reproduces the last SVT input like the reference's does
+        Wg, Wo = (s.U * s.S) @ s.Vt, (ref.s.U * ref.s.S) @ ref.s.Vt
+        assert relF(Wg, Wo) < 1e-7
 
 
 @pytest.mark.parametrize("M,N,r,kw", [(2000, 64, 5, {}), (20000, 256, 10, {"nonnegA": True}), (12000, 128, 20, {})])
-def test_rpca_converges_like_the_reference(M, N, r, kw):
+def test_rpca_converges_like_the_reference(M, N, r, kw, monkeypatch):
     D = T.synth.lowrank_sparse_np(M, N, r, 0.05, seed=4, nonneg=bool(kw.get("nonnegA")))
-    A, E, s, sv, info = T.rpca(D, return_info=True, **kw)
     ref = O.rpca(D, **kw)
-    assert info["converged"] and info["iters"] == ref.iters
-    assert relF(A, ref.A) < TOL and relF(E, ref.E) < TOL
-    assert np.linalg.norm(D - A - E) / np.linalg.norm(D) < SQRT_EPS
-    # exact cost evaluation (verbose path) reproduces the reference's cost sequence
-    _, _, _, _, info2 = T.rpca(D, return_info=True, exact_cost=True, want_svd=False, **kw)
-    assert info2["iters"] == ref.iters
-    assert np.allclose(info2["hist"][:, 2], ref.hist[:, 2], rtol=1e-6)
+    for fused in (("0", "1") if N == 256 else ("0",)):
+        monkeypatch.setenv("TLSQ_FUSED", fused)
+        A, E, s, sv, info = T.rpca(D, return_info=True, **kw)
+        assert info["converged"] and info["iters"] == ref.iters
+        assert relF(A, ref.A) < TOL and relF(E, ref.E) < TOL
+        assert np.linalg.norm(D - A - E) / np.linalg.norm(D) < SQRT_EPS
+        # exact cost evaluation (verbose path) reproduces the reference's cost sequence
+        _, _, _, _, info2 = T.rpca(D, return_info=True, exact_cost=True, want_svd=False, **kw)
+        assert info2["iters"] == ref.iters
+        assert np.allclose(info2["hist"][:, 2], ref.hist[:, 2], rtol=1e-6)
+    monkeypatch.delenv("TLSQ_FUSED")
 
 
 def test_max_iterations_warning_and_outputs():
@@ -198,10 +215,11 @@ def test_fused_pipeline_equals_two_kernel_pipeline(monkeypatch):
     """n = 256: the one-pass cluster kernel (fused.cu) against the streaming epilogue + SYRK pipeline it replaces, and
     the implicit-Hankel / in-place-Y / factored-unhankel variants of lowrankfilter against the oracle."""
     D = T.synth.lowrank_sparse_np(16384, 256, 7, 0.05, seed=9)
+    monkeypatch.setenv("TLSQ_FUSED", "1")
     A1, E1, s1, sv1, i1 = T.rpca(D, return_info=True)
-    monkeypatch.setenv("TLSQ_NO_FUSED", "1")
+    monkeypatch.setenv("TLSQ_FUSED", "0")
     A2, E2, s2, sv2, i2 = T.rpca(D, return_info=True)
-    monkeypatch.delenv("TLSQ_NO_FUSED")
+    monkeypatch.setenv("TLSQ_FUSED", "1")
     assert i1["iters"] == i2["iters"] and sv1 == sv2
     assert relF(A1, A2) < 1e-12 and relF(E1, E2) < 1e-12 and np.array_equal(E1 != 0, E2 != 0)
     assert np.allclose(s1.S, s2.S, rtol=0, atol=1e-12 * s2.S[0])
@@ -213,6 +231,11 @@ def test_fused_pipeline_equals_two_kernel_pipeline(monkeypatch):
     yf2, info2 = T.lowrankfilter(yn, 256, return_info=True)
     monkeypatch.delenv("TLSQ_INPLACE_Y")
     assert relF(yf2, yo) < TOL and info2["iters"] == info["iters"]
+    monkeypatch.setenv("TLSQ_FUSED_WS", "1")                              # warp-specialised variant of the kernel
+    yf4, info4 = T.lowrankfilter(yn, 256, return_info=True)
+    monkeypatch.delenv("TLSQ_FUSED_WS")
+    assert relF(yf4, yo) < TOL and info4["iters"] == info["iters"]
+    monkeypatch.delenv("TLSQ_FUSED")
     yf3 = T.lowrankfilter(yn[:-1], 256)                                   # odd row count: two-kernel pipeline
     assert relF(yf3, O.lowrankfilter(yn[:-1], 256)) < TOL
 

@@ -29,6 +29,7 @@ def conv(M, N, r, **kw):
     _, _, _, _, info2 = T.rpca(D, return_info=True, exact_cost=True, want_svd=False, **kw)
     print(f"      exact-cost iters {info2['iters']} cost ok={np.allclose(info2['hist'][:,2], ref.hist[:info2['iters'],2], rtol=1e-6) if info2['iters']==ref.iters else None}", flush=True)
 
+os.environ["TLSQ_FUSED"] = "1"
 print("fused eligible path", flush=True)
 case(8192, 256, 10, 14)
 case(20002, 256, 10, 12, nonnegA=True, nonnegE=True)
@@ -45,7 +46,16 @@ os.environ["TLSQ_INPLACE_Y"] = "1"
 yf2, info2 = T.lowrankfilter(yn, 256, return_info=True)
 print(f"  in-place Y: rel={relF(yf2, yo):.2e} iters={info2['iters']}", flush=True)
 del os.environ["TLSQ_INPLACE_Y"]
-os.environ["TLSQ_NO_FUSED"] = "1"
+os.environ["TLSQ_FUSED"] = "0"
 yf3, info3 = T.lowrankfilter(yn, 256, return_info=True)
 print(f"  two-kernel path: rel={relF(yf3, yo):.2e} iters={info3['iters']}", flush=True)
-del os.environ["TLSQ_NO_FUSED"]
+os.environ["TLSQ_FUSED"] = "1"
+# odd number of Hankel rows on the one-pass path (padded leading dimension of Y / T)
+y, yn = T.synth.sinusoid_np(12256, seed=3, noise=0.05)
+yo = O.lowrankfilter(yn, 256)
+yf, info = T.lowrankfilter(yn, 256, return_info=True)
+print(f"lowrankfilter n=256 Ns=12256 (K odd): rel={relF(yf, yo):.2e} iters={info['iters']}", flush=True)
+os.environ["TLSQ_INPLACE_Y"] = "1"
+yf, info = T.lowrankfilter(yn, 256, return_info=True)
+print(f"  in-place Y: rel={relF(yf, yo):.2e} iters={info['iters']}", flush=True)
+del os.environ["TLSQ_INPLACE_Y"]

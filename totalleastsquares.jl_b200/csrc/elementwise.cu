@@ -26,14 +26,14 @@ maxabs_kernel(const MatSrc D, int64_t M, int64_t N, double* __restrict__ out) {
 template <bool HANKEL>
 __global__ void __launch_bounds__(256)
 init_ya_kernel(const MatSrc D, int64_t M, int64_t N, double dual, double* __restrict__ Y, double* __restrict__ A,
-               double* __restrict__ W, double im, double eps, int nonnegE) {
+               double* __restrict__ W, double im, double eps, int nonnegE, int64_t ldy) {
     const int64_t total = M * N;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = idx % M, col = idx / M;
         const double d = src_at<HANKEL>(D, row, col);
         const double y = __ddiv_rn(d, dual);                         // Y ./= dual_norm   (:181)
-        Y[idx] = y;
+        Y[col * ldy + row] = y;
         if (A) A[idx] = 0.0;
         if (W) {
             double e, w;
@@ -215,10 +215,11 @@ cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, do
 
 cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A,
                            double* W, double im, double eps, int nonnegE, int sm_count, cudaStream_t st,
-                           int64_t* launches) {
+                           int64_t* launches, int64_t ldy) {
     const int grid = stream_grid(M * N, sm_count);
-    if (hankel) init_ya_kernel<true><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A, W, im, eps, nonnegE);
-    else init_ya_kernel<false><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A, W, im, eps, nonnegE);
+    if (ldy <= 0) ldy = M;
+    if (hankel) init_ya_kernel<true><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A, W, im, eps, nonnegE, ldy);
+    else init_ya_kernel<false><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A, W, im, eps, nonnegE, ldy);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

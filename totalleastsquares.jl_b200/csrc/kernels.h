@@ -194,6 +194,7 @@ struct FusedArgs {
     int gram_of;            // FusedGram
     double* partial;        // workspace, fused_partial_doubles(sm_count) doubles
     double* zpart;          // workspace inside partial (set by the launcher)
+    const double* VpT;      // packed V_{k-1}' scratch inside partial (set by the launcher)
 };
 size_t fused_partial_doubles(int sm_count);
 bool fused_eligible(const MatSrc& D, bool hankel, int64_t M, int64_t N);
@@ -209,7 +210,7 @@ cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, do
 // W (optional) = SVT input of the first iteration: (D - E_1) + Y_0/mu_1 with A_0 = 0
 cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A /*nullable*/,
                            double* W, double im, double eps, int nonnegE, int sm_count, cudaStream_t st,
-                           int64_t* launches);
+                           int64_t* launches, int64_t ldy = 0 /* leading dimension of Y; 0 = M */);
 // E = soft_th((D - A) + Y/mu, lambda/mu) (+ clamp)
 cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N, const double* A, const double* Y,
                              double im, double eps, int nonnegE, double* E, int sm_count, cudaStream_t st,

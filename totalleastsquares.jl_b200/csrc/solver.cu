@@ -233,8 +233,32 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // then neither read nor written inside the loop; it is materialised only for the outputs, or for good (one-way
     // switch to the dense representation) if the rank estimate ever exceeds 32.
     static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
-    bool fused = syrk_ok && !no_fact && fused_eligible(D, hankel, M, N);
+    // Pipeline choice: the one-pass kernel needs S (Y in place) .. 2 S of device memory, the two-kernel pipeline 3 S
+    // (Y x 2 + W); on B200 the two-kernel pipeline is currently the faster one when it fits (profiles/), so the
+    // one-pass kernel is taken when memory asks for it or when TLSQ_FUSED=1 forces it.
+    bool fused = !no_fact && fused_eligible(D, hankel, M, N);
+    if (fused && !syrk_ok && (o.A || o.E || o.U)) fused = false;   // padded leading dimension: factored outputs only
+    if (fused) {
+        const char* env_f = getenv("TLSQ_FUSED");
+        if (env_f) fused = atoi(env_f) != 0;
+        else {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+                uint64_t reserved = 0, used = 0;
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+                if (reserved > used) free_b += (size_t)(reserved - used);
+            }
+            size_t need = 3 * mn * 8 + ((size_t)4 << 30);
+            if (o.A) need += 0;                 // outputs are caller-allocated
+            fused = need > free_b;
+        }
+    }
     bool use_w = syrk_ok && !fused;
+    // the one-pass kernel moves Y / T tiles with TMA (16-byte strides): an odd row count gets a padded leading dimension
+    const int64_t ldp = fused ? M + (M & 1) : M;
     bool fact = (use_w || fused) && !no_fact;
     DevBuf bW, bT0, bT1, bV0, bV1, bFp;
     double* Wbuf = nullptr;
@@ -249,16 +273,16 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     double* Vb[2] = {nullptr, nullptr};
     int svpb[2] = {0, 0};
     if (fact) {
-        CK(bT0.alloc((size_t)M * kStreamMaxRank * 8, st)); CK(bT1.alloc((size_t)M * kStreamMaxRank * 8, st));
+        CK(bT0.alloc((size_t)ldp * kStreamMaxRank * 8, st)); CK(bT1.alloc((size_t)ldp * kStreamMaxRank * 8, st));
         CK(bV0.alloc((size_t)N * kStreamMaxRank * 8, st)); CK(bV1.alloc((size_t)N * kStreamMaxRank * 8, st));
         Tb[0] = bT0.as<double>(); Tb[1] = bT1.as<double>(); Vb[0] = bV0.as<double>(); Vb[1] = bV1.as<double>();
-        CK(cudaMemsetAsync(Tb[0], 0, (size_t)M * kStreamMaxRank * 8, st));
-        CK(cudaMemsetAsync(Tb[1], 0, (size_t)M * kStreamMaxRank * 8, st));
+        CK(cudaMemsetAsync(Tb[0], 0, (size_t)ldp * kStreamMaxRank * 8, st));
+        CK(cudaMemsetAsync(Tb[1], 0, (size_t)ldp * kStreamMaxRank * 8, st));
     }
     FusedArgs fa = {};
     if (fused) {
         CK(bFp.alloc(fused_partial_doubles(sms) * 8, st));
-        fa.D = D; fa.M = M; fa.ldy = M; fa.ldt = M; fa.nonnegA = nonnegA; fa.nonnegE = nonnegE;
+        fa.D = D; fa.M = M; fa.ldy = ldp; fa.ldt = ldp; fa.nonnegA = nonnegA; fa.nonnegE = nonnegE;
         fa.partial = bFp.as<double>();
         fa.zpart = fa.partial + (size_t)(sms / 2) * n * n;
     }
@@ -296,8 +320,8 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             inplace_y = need > free_b;
         }
     }
-    CK(bY0.alloc(mn * 8, st));
-    if (!inplace_y) CK(bY1.alloc(mn * 8, st));
+    CK(bY0.alloc((size_t)ldp * N * 8, st));
+    if (!inplace_y) CK(bY1.alloc((size_t)ldp * N * 8, st));
     double* Ybuf[2] = {bY0.as<double>(), inplace_y ? bY0.as<double>() : bY1.as<double>()};
     CK(bPart.alloc(part_bytes, st));
     CK(bG.alloc(((size_t)n * n + 8) * 8, st)); CK(bG2.alloc(((size_t)n * n + 8) * 8, st));
@@ -401,7 +425,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     {
         Phase ph(h, TLSQ_PHASE_INIT);
         CK(launch_init_ya(D, hankel, M, N, dual_norm, Ybuf[0], fact ? nullptr : Abuf[0], fused ? nullptr : Wbuf,
-                          1.0 / mu, p.lambda / mu, nonnegE, sms, st, L));                // Y ./= dual_norm :181
+                          1.0 / mu, p.lambda / mu, nonnegE, sms, st, L, ldp));           // Y ./= dual_norm :181
         if (fused) {
             // Gram of the first SVT input W_1 = (D - E_1) + Y_0/mu_1 (A_0 = 0), formed on the fly
             FusedArgs f1 = fa;
@@ -476,6 +500,9 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         const bool want_z = (use_w || fused) && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
         if (fused && (svp > kFusedMaxRank || svpb[cur] > kFusedMaxRank)) {
             // rank estimate beyond the fused kernel: materialise W_k once and continue on the streaming pipeline
+            if (ldp != M || inplace_y || !syrk_ok)
+                return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: rank estimate %d exceeds the one-pass kernel's %d and the "
+                               "streaming pipeline cannot take over (padded / in-place dual variable)", svp, kFusedMaxRank);
             CK(ensure_w());
             EpiArgs wa = {};
             wa.D = D; wa.Yp = Ybuf[cur]; wa.Tp = Tb[cur]; wa.Vp = Vb[cur]; wa.svp_prev = svpb[cur];
@@ -669,7 +696,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         // Factored iterate: ONE pass produces A_k, E_k and (for U) the last SVT input W_k from
         // (T_{k-1}, V_{k-1}, Y_{k-1}) and (T_k, V_k); W_k lands in the W buffer, which is free now.
         if (o.uh_sum)
-            CK(launch_unhankel_factors(Tb[last_idx], M, Vb[last_idx], svpb[last_idx], nonnegA, o.uh_r0, M, N, o.uh_Ns,
+            CK(launch_unhankel_factors(Tb[last_idx], ldp, Vb[last_idx], svpb[last_idx], nonnegA, o.uh_r0, M, N, o.uh_Ns,
                                        o.uh_sum, sms, st, L));
         if (o.U) CK(ensure_w());
         if (o.E || o.U) {
@@ -880,7 +907,8 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
         const int64_t r0 = h->rank * base + (h->rank < rem ? h->rank : rem);
         const int64_t Kl = base + (h->rank < rem ? 1 : 0);
         if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && Kl >= 1 &&
-            syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), Kl, n, Kl)) {
+            (syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), Kl, n, Kl) ||
+             fused_eligible(MatSrc{y + r0, 1}, true, Kl, n))) {
             CKR(check_rpca_args(Kl, n, p));
             DevBuf bSum;
             CK(bSum.alloc((size_t)Ns * 8, st));
