@@ -16,7 +16,10 @@ dist.init_process_group("nccl", device_id=dev)
 T.init_distributed(lr)
 relF = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 ok = True
-for (M, N, r, kw, its) in [(16384, 256, 10, {"nonnegA": True}, 10), (9000, 128, 5, {}, 10), (3000, 40, 3, {}, 8)]:
+for (M, N, r, kw, its) in [(16384, 256, 10, {"nonnegA": True}, 10), (16384, 256, 10, {"nonnegA": True, "fused": 1}, 10),
+                           (9000, 128, 5, {}, 10), (3000, 40, 3, {}, 8)]:
+    kw = dict(kw)
+    os.environ["TLSQ_FUSED"] = "1" if kw.pop("fused", 0) else "0"       # n = 256: both per-iteration pipelines
     D = T.synth.lowrank_sparse_np(M, N, r, 0.05, seed=M + N, nonneg=bool(kw.get("nonnegA")))
     r0, r1 = T.synth.shard_rows(M, world, rank, align=2)
     Dl = torch.from_numpy(np.ascontiguousarray(D[r0:r1].T)).to(dev).t()
@@ -33,11 +36,14 @@ for (M, N, r, kw, its) in [(16384, 256, 10, {"nonnegA": True}, 10), (9000, 128, 
 D = T.synth.lowrank_sparse_np(20000, 256, 10, 0.05, seed=4, nonneg=True)
 r0, r1 = T.synth.shard_rows(20000, world, rank, align=2)
 Dl = torch.from_numpy(np.ascontiguousarray(D[r0:r1].T)).to(dev).t()
-A, E, s, sv, info = T.rpca(Dl, nonnegA=True, return_info=True, want_svd=False)
 ref = O.rpca(D, nonnegA=True)
-good = info["iters"] == ref.iters and relF(A.cpu().numpy(), ref.A[r0:r1]) < 1e-9
-ok &= good
-print(f"[rank {rank}] converge iters {info['iters']}/{ref.iters} ok={good}", flush=True)
+for fused in ("0", "1"):
+    os.environ["TLSQ_FUSED"] = fused
+    A, E, s, sv, info = T.rpca(Dl, nonnegA=True, return_info=True, want_svd=False)
+    good = info["iters"] == ref.iters and relF(A.cpu().numpy(), ref.A[r0:r1]) < 1e-9
+    ok &= good
+    print(f"[rank {rank}] converge (fused={fused}) iters {info['iters']}/{ref.iters} ok={good}", flush=True)
+del os.environ["TLSQ_FUSED"]
 # Grassmann averages, d sharded
 X, q0 = T.synth.ga_data_np(8000, 200, 6, seed=3)
 a0, a1 = T.synth.shard_rows(8000, world, rank)
@@ -60,6 +66,18 @@ for (nn, lag) in [(100, 1), (37, 3)]:
     good = err < 1e-9
     ok &= good
     print(f"[rank {rank}] lowrankfilter n={nn} lag={lag} iters {inf['iters']} rel {err:.1e} ok={good}", flush=True)
+# n = 256: factored unhankel, one-pass kernel on the sharded implicit Hankel matrix (when the shard is tall enough)
+y, yn = T.synth.sinusoid_np(24831, seed=7, noise=0.05)
+yd = torch.from_numpy(yn).to(dev)
+yo = O.lowrankfilter(yn, 256)
+for fused in ("0", "1"):
+    os.environ["TLSQ_FUSED"] = fused
+    yf, inf = T.lowrankfilter(yd, 256, return_info=True)
+    err = relF(yf.cpu().numpy(), yo)
+    good = err < 1e-9
+    ok &= good
+    print(f"[rank {rank}] lowrankfilter n=256 (fused={fused}) iters {inf['iters']} rel {err:.1e} ok={good}", flush=True)
+del os.environ["TLSQ_FUSED"]
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("MGPU_CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)

@@ -7,38 +7,54 @@ namespace tlsq {
 
 namespace {
 
-template <bool HANKEL>
+// max |x_i| over a contiguous array (dense D with ld == M, or the signal span of an implicit Hankel matrix: every
+// sample y[0 .. (M-1) lag + N - 1] appears in H because lag <= N, src/robustPCA.jl:80)
 __global__ void __launch_bounds__(256)
-maxabs_kernel(const MatSrc D, int64_t M, int64_t N, double* __restrict__ out) {
-    const int64_t total = M * N;
-    double m = 0.0;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx % M, col = idx / M;
-        m = fmax(m, fabs(src_at<HANKEL>(D, row, col)));
+maxabs_linear_kernel(const double* __restrict__ x, int64_t total, double* __restrict__ out) {
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx + 3 * stride < total; idx += 4 * stride) {
+        m0 = fmax(m0, fabs(__ldg(x + idx)));
+        m1 = fmax(m1, fabs(__ldg(x + idx + stride)));
+        m2 = fmax(m2, fabs(__ldg(x + idx + 2 * stride)));
+        m3 = fmax(m3, fabs(__ldg(x + idx + 3 * stride)));
     }
-    m = warp_max(m);
+    for (; idx < total; idx += stride) m0 = fmax(m0, fabs(__ldg(x + idx)));
+    double m = warp_max(fmax(fmax(m0, m1), fmax(m2, m3)));
     // non-negative doubles order like their bit patterns
     if ((threadIdx.x & 31) == 0)
         atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
 }
 
+// dense D with a leading dimension > M: thread <-> row, loop over the columns (no 64-bit divisions)
+__global__ void __launch_bounds__(256)
+maxabs_kernel(const MatSrc D, int64_t M, int64_t N, double* __restrict__ out) {
+    double m = 0.0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < M; row += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t col = 0; col < N; ++col) m = fmax(m, fabs(__ldg(D.p + col * D.ld + row)));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+// Y = D / dual (:181), A = 0, and (optionally) the first SVT input W_1; thread <-> row, coalesced column sweeps
 template <bool HANKEL>
 __global__ void __launch_bounds__(256)
 init_ya_kernel(const MatSrc D, int64_t M, int64_t N, double dual, double* __restrict__ Y, double* __restrict__ A,
                double* __restrict__ W, double im, double eps, int nonnegE, int64_t ldy) {
-    const int64_t total = M * N;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx % M, col = idx / M;
-        const double d = src_at<HANKEL>(D, row, col);
-        const double y = __ddiv_rn(d, dual);                         // Y ./= dual_norm   (:181)
-        Y[col * ldy + row] = y;
-        if (A) A[idx] = 0.0;
-        if (W) {
-            double e, w;
-            alm_ew(d, 0.0, y, im, eps, nonnegE, e, w);               // first SVT input   (:188-192)
-            W[idx] = w;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < M; row += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll 4
+        for (int64_t col = 0; col < N; ++col) {
+            const double d = src_at<HANKEL>(D, row, col);
+            const double y = __ddiv_rn(d, dual);                         // Y ./= dual_norm   (:181)
+            Y[col * ldy + row] = y;
+            if (A) A[col * M + row] = 0.0;
+            if (W) {
+                double e, w;
+                alm_ew(d, 0.0, y, im, eps, nonnegE, e, w);               // first SVT input   (:188-192)
+                W[col * M + row] = w;
+            }
         }
     }
 }
@@ -206,9 +222,12 @@ inline int stream_grid(int64_t total, int sm_count) {
 
 cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, double* out, int sm_count,
                           cudaStream_t st, int64_t* launches) {
-    const int grid = stream_grid(M * N, sm_count);
-    if (hankel) maxabs_kernel<true><<<grid, 256, 0, st>>>(D, M, N, out);
-    else maxabs_kernel<false><<<grid, 256, 0, st>>>(D, M, N, out);
+    if (hankel || D.ld == M) {
+        const int64_t total = hankel ? (M - 1) * D.ld + N : M * N;
+        maxabs_linear_kernel<<<stream_grid(total / 4 + 1, sm_count), 256, 0, st>>>(D.p, total, out);
+    } else {
+        maxabs_kernel<<<stream_grid(M, sm_count), 256, 0, st>>>(D, M, N, out);
+    }
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -216,7 +235,7 @@ cudaError_t launch_maxabs(const MatSrc& D, bool hankel, int64_t M, int64_t N, do
 cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, double dual, double* Y, double* A,
                            double* W, double im, double eps, int nonnegE, int sm_count, cudaStream_t st,
                            int64_t* launches, int64_t ldy) {
-    const int grid = stream_grid(M * N, sm_count);
+    const int grid = stream_grid(M, sm_count);
     if (ldy <= 0) ldy = M;
     if (hankel) init_ya_kernel<true><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A, W, im, eps, nonnegE, ldy);
     else init_ya_kernel<false><<<grid, 256, 0, st>>>(D, M, N, dual, Y, A, W, im, eps, nonnegE, ldy);

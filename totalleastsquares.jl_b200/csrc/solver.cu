@@ -106,6 +106,8 @@ struct tlsq_handle {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // output pass of the finalisation overlaps the full eigensolver
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
     void* comm = nullptr;
     int nranks = 1;
@@ -251,8 +253,8 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                 cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
                 if (reserved > used) free_b += (size_t)(reserved - used);
             }
-            size_t need = 3 * mn * 8 + ((size_t)4 << 30);
-            if (o.A) need += 0;                 // outputs are caller-allocated
+            // two-kernel pipeline: Y x 2, W and (late iterations) Z  ->  4 S + workspace
+            const size_t need = 4 * mn * 8 + mn * 8 / 4 + ((size_t)4 << 30);
             fused = need > free_b;
         }
     }
@@ -679,6 +681,11 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
 
     // ---- outputs (:238) ----------------------------------------------------------------------------------
     Phase ph_final(h, TLSQ_PHASE_FINALIZE);
+    bool joined = true;
+    // fork point of the side stream (see below); the eigensolver is enqueued FIRST so that its cluster kernel gets its
+    // SMs before the bandwidth-bound output pass fills the machine
+    if (fact && o.U) CK(ensure_w());          // allocated in stream order BEFORE the fork point
+    CK(cudaEventRecord(h->ev_fork, st));
     if (fast_ok && last_was_fast && (o.S || o.Vt || o.U)) {
         // the fast path only carries the dominant block; the returned SVD (:238) needs the full spectrum of the last W.
         // On the fused path G already holds the Gram of W_{k+1}: rebuild W_k'W_k from (Y_{k-1}, T_{k-1}).
@@ -694,20 +701,28 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     }
     if (fact) {
         // Factored iterate: ONE pass produces A_k, E_k and (for U) the last SVT input W_k from
-        // (T_{k-1}, V_{k-1}, Y_{k-1}) and (T_k, V_k); W_k lands in the W buffer, which is free now.
+        // (T_{k-1}, V_{k-1}, Y_{k-1}) and (T_k, V_k); W_k lands in the W buffer, which is free now.  The pass is
+        // HBM-bound and independent of the full eigen-decomposition below (latency-bound, a few SMs): it runs on the
+        // side stream, concurrently.
+        cudaStream_t ss = h->side;
+        CK(cudaStreamWaitEvent(ss, h->ev_fork, 0));
         if (o.uh_sum)
             CK(launch_unhankel_factors(Tb[last_idx], ldp, Vb[last_idx], svpb[last_idx], nonnegA, o.uh_r0, M, N, o.uh_Ns,
-                                       o.uh_sum, sms, st, L));
-        if (o.U) CK(ensure_w());
+                                       o.uh_sum, sms, ss, L));
         if (o.E || o.U) {
             EpiArgs fe = {};
             fe.D = D; fe.Yp = Ybuf[prev_idx]; fe.Tp = Tb[prev_idx]; fe.Vp = Vb[prev_idx]; fe.svp_prev = svpb[prev_idx];
             fe.Tn = Tb[last_idx]; fe.Vs = Vb[last_idx]; fe.An = o.A; fe.Eout = o.E; fe.M = M; fe.N = N; fe.ldw = M;
             fe.im = im_last; fe.eps = eps_last; fe.nonnegA = nonnegA; fe.nonnegE = nonnegE;
-            CK(launch_final_from_factors(fe, hankel, svpb[last_idx], o.U ? Wbuf : nullptr, sms, st, L));
+            CK(launch_final_from_factors(fe, hankel, svpb[last_idx], o.U ? Wbuf : nullptr, sms, ss, L));
         } else if (o.A) {
-            CK(launch_fact_to_dense(Tb[last_idx], Vb[last_idx], svpb[last_idx], M, N, nonnegA, o.A, sms, st, L));
+            CK(launch_fact_to_dense(Tb[last_idx], Vb[last_idx], svpb[last_idx], M, N, nonnegA, o.A, sms, ss, L));
         }
+        CK(cudaEventRecord(h->ev_join, ss));
+        joined = false;
+    }
+    if (!joined) { CK(cudaStreamWaitEvent(st, h->ev_join, 0)); joined = true; }
+    if (fact) {
         if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
         if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
         if (o.U) {
@@ -1006,6 +1021,9 @@ int tlsq_create(int device, tlsq_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double)));
     // keep freed blocks cached in the stream-ordered pool between solves
     cudaMemPool_t pool;
@@ -1022,6 +1040,9 @@ int tlsq_destroy(tlsq_handle* h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     delete h;
     return TLSQ_OK;

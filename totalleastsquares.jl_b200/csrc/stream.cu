@@ -32,7 +32,9 @@ __device__ __forceinline__ double dot_rp(const double (&t)[RP > 0 ? RP : 1], con
     return acc;
 }
 
-template <int RP, bool HANKEL, bool FACT>
+// PH: 0 = both loops in one kernel; 1 = only T = (W V_r) .* f (written to a.Tn); 2 = only the element-wise pass (T_k read
+// back from a.Tn).  The split form (1 then 2, FACT only) runs each loop at a higher occupancy.
+template <int RP, bool HANKEL, bool FACT, int PH>
 __global__ void __launch_bounds__(128)
 alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
     extern __shared__ double Vsm[];            // [N][RP]  (+ [N][RP] of V_{k-1} when FACT)
@@ -43,7 +45,7 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
     for (int idx = threadIdx.x; idx < N * RP; idx += blockDim.x) {
         const int j = idx % N, c = idx / N;
         Vsm[j * RP + c] = c < svp ? __ldg(a.Vs + (int64_t)c * N + j) : 0.0;
-        if (FACT) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + j) : 0.0;
+        if (FACT && PH != 1) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + j) : 0.0;
     }
     __syncthreads();
     double zz = 0.0;
@@ -56,7 +58,14 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
         double tp[RP > 0 ? RP : 1];
 #pragma unroll
         for (int c = 0; c < RP; ++c) tr[c] = 0.0;
-        if (RP > 0) {
+        if (RP > 0 && PH == 2) {
+#pragma unroll
+            for (int c = 0; c < RP; ++c) {
+                tr[c] = c < svp ? __ldg(a.Tn + (int64_t)c * a.M + row) : 0.0;
+                tp[c] = c < a.svp_prev ? __ldg(a.Tp + (int64_t)c * a.M + row) : 0.0;
+            }
+        }
+        if (RP > 0 && PH != 2) {
             constexpr int UW = 8;
             double wv[UW], wn[UW];
 #pragma unroll
@@ -86,11 +95,12 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
             if (FACT) {
 #pragma unroll
                 for (int c = 0; c < RP; ++c) {
-                    tp[c] = c < a.svp_prev ? __ldg(a.Tp + (int64_t)c * a.M + row) : 0.0;
+                    if (PH == 0) tp[c] = c < a.svp_prev ? __ldg(a.Tp + (int64_t)c * a.M + row) : 0.0;
                     a.Tn[(int64_t)c * a.M + row] = tr[c];
                 }
             }
         }
+        if (PH == 1) continue;
         double dv[UB], av[UB], yv[UB], dn[UB], an_[UB], yn_[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
@@ -203,25 +213,35 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
     }
 }
 
-inline int rp_of(int svp) { return (svp + 7) & ~7; }
+// padded rank of the specialised kernels: 0, 4, 8, 12, 16, 24, 32
+inline int rp_of(int svp) { return svp <= 16 ? ((svp + 3) & ~3) : ((svp + 7) & ~7); }
 
 template <int RP>
 cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count, cudaStream_t st) {
     const bool fact = a.Tn != nullptr;
-    const size_t smem = (size_t)a.N * RP * sizeof(double) * (fact ? 2 : 1);
+    static const bool split_env = getenv("TLSQ_STREAM_SPLIT") ? atoi(getenv("TLSQ_STREAM_SPLIT")) != 0 : true;
+    const bool split = fact && split_env && RP > 0;
     int64_t blocks = (a.M + 127) / 128;
     int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     cudaError_t e = cudaSuccess;
-#define TLSQ_STREAM_LAUNCH(H, F)                                                                                  \
+#define TLSQ_STREAM_LAUNCH(H, F, PH, SM)                                                                          \
     do {                                                                                                          \
-        auto kern = alm_stream_kernel<RP, H, F>;                                                                  \
-        if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(a, W, svp);                               \
+        auto kern = alm_stream_kernel<RP, H, F, PH>;                                                              \
+        const size_t smem_ = (SM);                                                                                \
+        if (smem_ > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
+        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem_, st>>>(a, W, svp);                              \
     } while (0)
-    if (hankel) { if (fact) TLSQ_STREAM_LAUNCH(true, true); else TLSQ_STREAM_LAUNCH(true, false); }
-    else        { if (fact) TLSQ_STREAM_LAUNCH(false, true); else TLSQ_STREAM_LAUNCH(false, false); }
+    const size_t sm1 = (size_t)a.N * RP * sizeof(double);
+    if (split) {
+        if (hankel) { TLSQ_STREAM_LAUNCH(true, true, 1, sm1); if (e == cudaSuccess) TLSQ_STREAM_LAUNCH(true, true, 2, 2 * sm1); }
+        else        { TLSQ_STREAM_LAUNCH(false, true, 1, sm1); if (e == cudaSuccess) TLSQ_STREAM_LAUNCH(false, true, 2, 2 * sm1); }
+    } else if (hankel) {
+        if (fact) TLSQ_STREAM_LAUNCH(true, true, 0, 2 * sm1); else TLSQ_STREAM_LAUNCH(true, false, 0, sm1);
+    } else {
+        if (fact) TLSQ_STREAM_LAUNCH(false, true, 0, 2 * sm1); else TLSQ_STREAM_LAUNCH(false, false, 0, sm1);
+    }
 #undef TLSQ_STREAM_LAUNCH
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
@@ -264,7 +284,9 @@ cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, int svp, b
     const int rp = rp_of(fact && a.svp_prev > svp ? a.svp_prev : svp);
     switch (rp) {
         case 0:  e = launch_stream_rp<0>(a, W, svp, hankel, sm_count, st); break;
+        case 4:  e = launch_stream_rp<4>(a, W, svp, hankel, sm_count, st); break;
         case 8:  e = launch_stream_rp<8>(a, W, svp, hankel, sm_count, st); break;
+        case 12: e = launch_stream_rp<12>(a, W, svp, hankel, sm_count, st); break;
         case 16: e = launch_stream_rp<16>(a, W, svp, hankel, sm_count, st); break;
         case 24: e = launch_stream_rp<24>(a, W, svp, hankel, sm_count, st); break;
         default: e = launch_stream_rp<32>(a, W, svp, hankel, sm_count, st); break;
@@ -280,7 +302,9 @@ cudaError_t launch_fact_to_dense(const double* T, const double* V, int svp, int6
     cudaError_t e;
     switch (rp_of(svp)) {
         case 0:  e = launch_fact_rp<0, 0>(a, T, V, svp, false, A, sm_count, st); break;
+        case 4:  e = launch_fact_rp<4, 0>(a, T, V, svp, false, A, sm_count, st); break;
         case 8:  e = launch_fact_rp<8, 0>(a, T, V, svp, false, A, sm_count, st); break;
+        case 12: e = launch_fact_rp<12, 0>(a, T, V, svp, false, A, sm_count, st); break;
         case 16: e = launch_fact_rp<16, 0>(a, T, V, svp, false, A, sm_count, st); break;
         case 24: e = launch_fact_rp<24, 0>(a, T, V, svp, false, A, sm_count, st); break;
         default: e = launch_fact_rp<32, 0>(a, T, V, svp, false, A, sm_count, st); break;
@@ -296,7 +320,9 @@ cudaError_t launch_z_from_factors(const EpiArgs& a, bool hankel, int svp, double
     const int rp = rp_of(a.svp_prev > svp ? a.svp_prev : svp);
     switch (rp) {
         case 0:  e = launch_fact_rp<0, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 4:  e = launch_fact_rp<4, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
         case 8:  e = launch_fact_rp<8, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
+        case 12: e = launch_fact_rp<12, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
         case 16: e = launch_fact_rp<16, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
         case 24: e = launch_fact_rp<24, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
         default: e = launch_fact_rp<32, 1>(a, a.Tn, a.Vs, svp, hankel, Z, sm_count, st); break;
@@ -313,7 +339,9 @@ cudaError_t launch_final_from_factors(const EpiArgs& a, bool hankel, int svp, do
     const int rp = rp_of(a.svp_prev > svp ? a.svp_prev : svp);
     switch (rp) {
         case 0:  e = launch_fact_rp<0, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
+        case 4:  e = launch_fact_rp<4, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
         case 8:  e = launch_fact_rp<8, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
+        case 12: e = launch_fact_rp<12, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
         case 16: e = launch_fact_rp<16, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
         case 24: e = launch_fact_rp<24, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;
         default: e = launch_fact_rp<32, 2>(a, a.Tn, a.Vs, svp, hankel, Wout, sm_count, st); break;

@@ -54,21 +54,52 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
-// Warp -> output tiles.  Off-diagonal block: 4 x 2 warps, warp tile 32 x 64.  Diagonal block: only the 10 upper
-// 32 x 32 tiles are computed -- two warps own a 32 x 64 strip of row 0, six warps own one 32 x 32 tile each, placed
-// so that the four SM sub-partitions carry 3,3,2,2 tile units (a diagonal block costs 3/4 of an off-diagonal one and
-// gets proportionally fewer CTAs, see syrk_plan).
-__device__ __forceinline__ void warp_tiles(bool diag, int warp, int& a0, int& b0, int& nn) {
-    if (!diag) { a0 = 32 * (warp & 3); b0 = 64 * (warp >> 2); nn = 8; return; }
-    switch (warp) {
-        case 0: a0 = 0;  b0 = 0;  nn = 8; break;
-        case 1: a0 = 0;  b0 = 64; nn = 8; break;
-        case 2: a0 = 32; b0 = 32; nn = 4; break;
-        case 3: a0 = 32; b0 = 64; nn = 4; break;
-        case 4: a0 = 32; b0 = 96; nn = 4; break;
-        case 5: a0 = 64; b0 = 64; nn = 4; break;
-        case 6: a0 = 64; b0 = 96; nn = 4; break;
-        default: a0 = 96; b0 = 96; nn = 4; break;
+// Warp -> output tiles.  Off-diagonal block: 4 x 2 warps, warp tile 32 x 64 (32 DMMA accumulators).  Diagonal block:
+// only the 10 upper 32 x 32 tiles are computed; they are cut into 40 strips of 32 x 8 columns, enumerated tile row by
+// tile row, and warp w takes strips [5w, 5w + 5) -- 20 DMMAs per k-step on every warp (perfectly balanced, a diagonal
+// block costs 5/8 of an off-diagonal one and gets proportionally fewer CTAs, see syrk_plan).  A warp's strips span at
+// most two tile rows: the first n1 take their A fragments from tile row rowA, the others from rowB.
+struct DiagStrips { int rowA, rowB, n1; int cs[5]; };
+__device__ __forceinline__ DiagStrips diag_strips(int warp) {
+    DiagStrips d;
+    int n = 0, k = 0;
+    d.rowA = d.rowB = 0; d.n1 = 0;
+#pragma unroll
+    for (int arow = 0; arow < 4; ++arow)
+#pragma unroll
+        for (int c = 4 * arow; c < 16; ++c, ++n) {
+            if (n >= 5 * warp && n < 5 * warp + 5) {
+                if (k == 0) d.rowA = arow;
+                d.rowB = arow;
+                if (arow == d.rowA) d.n1 = k + 1;
+                d.cs[k++] = c;
+            }
+        }
+    return d;
+}
+
+// the first N1 strips use a1, the others a2 (N1 is per-warp constant: the switch keeps accumulator indexing static)
+template <int N1>
+__device__ __forceinline__ void diag_stage(double (&acc)[4][8][2], const uint8_t* pa, uint32_t aA, uint32_t aB,
+                                           const uint32_t (&bo)[5], const uint32_t (&koff)[4]) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint8_t* ph = pa + half * BOX_BYTES;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            double a1[4], a2[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                a1[mi] = *reinterpret_cast<const double*>(ph + aA + (uint32_t)mi * 1024u + koff[s4]);
+                if (N1 < 5) a2[mi] = *reinterpret_cast<const double*>(ph + aB + (uint32_t)mi * 1024u + koff[s4]);
+            }
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const double b = *reinterpret_cast<const double*>(ph + bo[s] + koff[s4]);
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][s][0], acc[mi][s][1], s < N1 ? a1[mi] : a2[mi], b);
+            }
+        }
     }
 }
 
@@ -97,8 +128,8 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
     const bool diag = (bi == bj);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    int a0, b0, nn;
-    warp_tiles(diag, warp, a0, b0, nn);
+    const int a0 = 32 * (warp & 3), b0 = 64 * (warp >> 2);       // off-diagonal warp tile
+    const DiagStrips ds = diag_strips(warp);
 
     if (tid == 0) {
 #pragma unroll
@@ -135,6 +166,10 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
     }
     const uint32_t a_col = (uint32_t)(a0 + g) * 128u;
     const uint32_t b_col = (uint32_t)(b0 + g) * 128u;
+    const uint32_t dA = (uint32_t)(32 * ds.rowA + g) * 128u, dB = (uint32_t)(32 * ds.rowB + g) * 128u;
+    uint32_t dbo[5];
+#pragma unroll
+    for (int s5 = 0; s5 < 5; ++s5) dbo[s5] = (uint32_t)(8 * ds.cs[s5] + g) * 128u;
 
     double acc[4][8][2];
 #pragma unroll
@@ -148,24 +183,31 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
         mbar_wait(&full_bar[s], parity);
         const uint8_t* pa = base + (size_t)s * STAGE_BYTES;
         const uint8_t* pb = diag ? pa : pa + PANEL_BYTES;
+        if (!diag) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                double a[4], b[8];
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    double a[4], b[8];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-                    a[mi] = *reinterpret_cast<const double*>(pa + half * BOX_BYTES + a_col + (uint32_t)mi * 1024u + koff[s4]);
+                    for (int mi = 0; mi < 4; ++mi)
+                        a[mi] = *reinterpret_cast<const double*>(pa + half * BOX_BYTES + a_col + (uint32_t)mi * 1024u + koff[s4]);
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni)
-                    if (ni < nn)
+                    for (int ni = 0; ni < 8; ++ni)
                         b[ni] = *reinterpret_cast<const double*>(pb + half * BOX_BYTES + b_col + (uint32_t)ni * 1024u + koff[s4]);
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni)
-                    if (ni < nn) {
+                    for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
                         for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                    }
+                }
+            }
+        } else {
+            switch (ds.n1) {
+                case 1: diag_stage<1>(acc, pa, dA, dB, dbo, koff); break;
+                case 2: diag_stage<2>(acc, pa, dA, dB, dbo, koff); break;
+                case 3: diag_stage<3>(acc, pa, dA, dB, dbo, koff); break;
+                case 4: diag_stage<4>(acc, pa, dA, dB, dbo, koff); break;
+                default: diag_stage<5>(acc, pa, dA, dB, dbo, koff); break;
             }
         }
         __syncthreads();                               // every warp is done with stage s -> refill it
@@ -173,16 +215,29 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
     }
 
     double* P = partial + ((size_t)plan.part_off[blk] + split) * (SB * SB);
+    if (!diag) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni)
-            if (ni < nn) {
+            for (int ni = 0; ni < 8; ++ni) {
                 const int il = a0 + 8 * mi + g;
                 const int jl = b0 + 8 * ni + 2 * t;
                 P[jl * SB + il] = acc[mi][ni][0];
                 P[(jl + 1) * SB + il] = acc[mi][ni][1];
             }
+    } else {
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5) {
+            const int ra = 32 * (s5 < ds.n1 ? ds.rowA : ds.rowB);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int il = ra + 8 * mi + g;
+                const int jl = 8 * ds.cs[s5] + 2 * t;
+                P[jl * SB + il] = acc[mi][s5][0];
+                P[(jl + 1) * SB + il] = acc[mi][s5][1];
+            }
+        }
+    }
 }
 
 // G[i,j] = G[j,i] = sum over the splits of block(i,j), fixed order; diagonal blocks only hold their upper 32-tiles
@@ -238,13 +293,13 @@ SyrkPlan syrk_plan(int64_t M, int64_t N, int sm_count) {
     p.nb = (int)((N + SB - 1) / SB);
     p.nblk = p.nb * (p.nb + 1) / 2;
     p.ntiles = (int)((M + SRS - 1) / SRS);
-    // CTAs per block proportional to the block's cost (off-diagonal 4 tile units per sub-partition, diagonal 3)
+    // CTAs per block proportional to the block's cost (off-diagonal: 32 DMMAs per warp and k-step, diagonal: 20)
     int ndiag = p.nb, noff = p.nblk - p.nb;
-    double unit = (double)sm_count / (4.0 * noff + 3.0 * ndiag);
+    double unit = (double)sm_count / (4.0 * noff + 2.5 * ndiag);
     int total = 0, blk = 0;
     for (int bi = 0; bi < p.nb; ++bi)
         for (int bj = bi; bj < p.nb; ++bj, ++blk) {
-            int ns = (int)((bi == bj ? 3.0 : 4.0) * unit);
+            int ns = (int)((bi == bj ? 2.5 : 4.0) * unit);
             if (ns < 1) ns = 1;
             if (ns > p.ntiles) ns = p.ntiles;
             p.nsplit_blk[blk] = ns;
