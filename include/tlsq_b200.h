@@ -45,7 +45,7 @@ extern "C" {
 /* rpca flag bits (reference kwargs, src/robustPCA.jl:162-166) */
 #define TLSQ_NONNEG_A     (1u << 0)  /* nonnegA=true  (:217-219)                                   */
 #define TLSQ_NONNEG_E     (1u << 1)  /* nonnegE=true  (:189-191)                                   */
-#define TLSQ_HANKEL       (1u << 2)  /* hankel=true   (:214-216,234-236)  -> TLSQ_ERR_UNSUPPORTED  */
+#define TLSQ_HANKEL       (1u << 2)  /* hankel=true   (:214-216,234-236)  single GPU only          */
 #define TLSQ_NO_NUKE_A    (1u << 3)  /* nukeA=false   (:209-213)                                   */
 #define TLSQ_EXACT_COST   (1u << 4)  /* evaluate opnorm(Z) exactly every iteration (needed only to print the
                                         verbose cost, :226); otherwise the stop test uses Frobenius brackets and
@@ -138,6 +138,23 @@ int tlsq_rpca_ga_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, 
 int tlsq_hankel_f64(tlsq_handle* h, const double* x, int64_t Ns, int64_t L, int64_t lag, double* H);
 /* y: Ns samples; y[t] = mean of all A[k,l] with k*lag + l == t (0 where no entry maps to t, :66)              */
 int tlsq_unhankel_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, double* y);
+
+/* ---- general forms of the three functions above: D channels (x / y: Ns x D column-major; the trajectory matrix is
+ * K x (L D) with H[k, l D + d] = x[k lag + l, d], src/robustPCA.jl:83-90; unhankel :53-68) and the sv > 0 plain-SSA
+ * branch of lowrankfilter (A = U[:,1:sv] S[1:sv] Vt[1:sv,:] of svd(H), :123-125; sv_ssa <= 0 selects rpca).
+ * D == 1 with sv_ssa <= 0 is forwarded to the implicit-Hankel path above; the other cases materialise H
+ * (single GPU).                                                                                                  */
+int tlsq_lowrankfilter_mc_f64(tlsq_handle* h, const double* y, int64_t Ns, int64_t D, int64_t n, int64_t lag,
+                              int64_t sv_ssa, double lambda, int64_t maxrank, int64_t iters, double tol, double rho,
+                              uint32_t flags, double* yf, int64_t* sv, int64_t* iters_done, int32_t* converged,
+                              double* hist);
+int tlsq_lowrankfilter_mc_f64_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t D, int64_t n, int64_t lag,
+                                  int64_t sv_ssa, double lambda, int64_t maxrank, int64_t iters, double tol, double rho,
+                                  uint32_t flags, double* yf, int64_t* sv, int64_t* iters_done, int32_t* converged,
+                                  double* hist);
+int tlsq_hankel_mc_f64(tlsq_handle* h, const double* x, int64_t Ns, int64_t D, int64_t L, int64_t lag, double* H);
+int tlsq_unhankel_mc_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, int64_t D,
+                         double* y);
 
 /* ---- building blocks exposed for tests and profiling (device pointers) ------------------------------------- */
 /* G (n x n, column-major) = X' X for X: M x n column-major, via the FP64 tensor-core (DMMA) SYRK kernel       */

@@ -144,6 +144,53 @@ def test_rpca_converges_like_the_reference(M, N, r, kw, monkeypatch):
     monkeypatch.delenv("TLSQ_FUSED")
 
 
+@pytest.mark.parametrize("Ns,L,kw", [(1000, 50, {"nukeA": False}), (600, 24, {}), (4500, 200, {"nukeA": False})])
+def test_rpca_hankel_true_matches_the_oracle(Ns, L, kw):
+    """hankel=true: soft_hankel! of the iterate every iteration and of E at the end (src/robustPCA.jl:9-21, 214-216,
+    234-236; reference tests test/runtests.jl:309-348)."""
+    rng = np.random.default_rng(Ns + L)
+    H = O.hankel(rng.standard_normal(Ns), L)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        A, E, s, sv, info = T.rpca(H, hankel=True, iters=15, tol=0.0, return_info=True, **kw)
+        ref = O.rpca(H, hankel=True, iters=15, tol=0.0, **kw)
+    assert relF(A, ref.A) < TOL and relF(E, ref.E) < TOL
+    assert np.array_equal(info["hist"][:, 1], ref.hist[:, 1])
+    A2, E2, _, _, info2 = T.rpca(H, hankel=True, return_info=True, **kw)
+    ref2 = O.rpca(H, hankel=True, **kw)
+    assert info2["iters"] == ref2.iters and relF(A2, ref2.A) < TOL
+    if kw.get("nukeA") is False:                                             # test/runtests.jl:331-332 (nukeA=false)
+        assert O.ishankel(A2) and O.ishankel(E2)
+
+
+def test_rtls_beats_tls_on_outliers():
+    """test/runtests.jl:203-235 (statistical, reduced): rtls = rpca([A y]; nukeA=false) + tls! on the returned SVD."""
+    rng = np.random.default_rng(3)
+    wins = 0
+    for _ in range(20):
+        x = rng.standard_normal(3)
+        A = rng.standard_normal((50, 3))
+        y = A @ x
+        An = A + 0.01 * rng.standard_normal(A.shape)
+        yn = y + 0.01 * rng.standard_normal(50)
+        An[rng.random(A.shape) < 0.05] += 10.0 * rng.standard_normal()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            xr = T.rtls(An, yn).ravel()
+            xo = O_rtls(An, yn).ravel()
+        assert np.allclose(xr, xo, rtol=1e-6, atol=1e-8)
+        xt = T.tls(An, yn).ravel()
+        wins += np.linalg.norm(xr - x) < np.linalg.norm(xt - x)
+    assert wins >= 14
+
+
+def O_rtls(A, y):
+    ref = O.rpca(np.hstack([A, y.reshape(-1, 1)]), nukeA=False)
+    V = ref.s.Vt.T
+    n = A.shape[1]
+    return -np.linalg.solve(V[n:, n:].T, V[:n, n:].T).T
+
+
 def test_max_iterations_warning_and_outputs():
     D = T.synth.lowrank_sparse_np(500, 20, 3, 0.05, seed=1)
     with pytest.warns(UserWarning, match="Maximum number of iterations"):
@@ -238,6 +285,42 @@ def test_fused_pipeline_equals_two_kernel_pipeline(monkeypatch):
     monkeypatch.delenv("TLSQ_FUSED")
     yf3 = T.lowrankfilter(yn[:-1], 256)                                   # odd row count: two-kernel pipeline
     assert relF(yf3, O.lowrankfilter(yn[:-1], 256)) < TOL
+
+
+def test_multichannel_and_ssa_forms():
+    """test/runtests.jl:361-376 (exact round trips incl. lag 2 and two channels), :401-405 (sv=2 plain SSA) and
+    :408-439 (multi-channel lowrankfilter) against the oracle and the reference's statistical bounds."""
+    rng = np.random.default_rng(11)
+    Tn = 1000
+    t = np.arange(1, Tn + 1)
+    qn = lambda x: x / np.quantile(np.abs(x), 0.9)
+    y = qn(np.sin(0.1 * t))
+    assert np.array_equal(T.unhankel(T.hankel(y, 2)), y)
+    assert np.array_equal(T.unhankel(T.hankel(y, 2, 2), 2, Tn), y)
+    yh = T.unhankel(T.hankel(y, 5, 2), 2, Tn)
+    assert np.allclose(yh[:-1], y[:-1])
+    Y2 = np.column_stack([y, rng.standard_normal(Tn)])
+    H = T.hankel(Y2, 5, 2)
+    assert np.array_equal(H, O.hankel(Y2, 5, 2))
+    yh = T.unhankel(H, 2, Tn, 2)
+    assert np.allclose(yh[:-1], Y2[:-1]) and np.allclose(yh, O.unhankel(H, 2, Tn, 2), rtol=0, atol=1e-14)
+    # plain SSA branch
+    noise = rng.standard_normal(Tn)
+    yf = T.lowrankfilter(y + noise, sv=2)
+    assert relF(yf, O.lowrankfilter(y + noise, sv=2)) < TOL
+    assert np.mean((y - qn(yf)) ** 2) / np.mean(noise ** 2) < 0.05
+    yf_w = T.lowrankfilter((y + noise)[:90], 40, sv=3)                      # K = 51 < n = 40?  no: wide when K < n D
+    assert relF(yf_w, O.lowrankfilter((y + noise)[:90], 40, sv=3)) < TOL
+    # multi-channel lowrankfilter
+    y1, y2 = np.sin(0.1 * t), np.sin(0.3 * t)
+    Y = np.column_stack([y1, y2 + 0.5 * y1])
+    Yn = Y + 0.1 * rng.standard_normal(Y.shape) + (rng.random(Y.shape) < 0.01) * 5 * rng.standard_normal(Y.shape)
+    Yf = T.lowrankfilter(Yn, 20)
+    assert Yf.shape == Y.shape and relF(Yf, O.lowrankfilter(Yn, 20)) < TOL
+    assert np.mean((Y - Yf) ** 2) / np.mean((Y - Yn) ** 2) < 0.05
+    yf1 = T.lowrankfilter(Yn[:, 0].copy(), 20)
+    assert np.mean((y1 - yf1) ** 2) / np.mean((y1 - Yf[:, 0]) ** 2) > 1.02   # joint filtering helps (:420-422)
+    assert relF(T.lowrankfilter(Yn, 12, lag=2, sv=4), O.lowrankfilter(Yn, 12, lag=2, sv=4)) < TOL
 
 
 @pytest.mark.parametrize("d,N,r", [(10, 40, 3), (40, 10, 5), (1000, 256, 4), (5000, 300, 3), (777, 1000, 2)])

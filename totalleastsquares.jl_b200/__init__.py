@@ -25,7 +25,7 @@ import numpy as np
 from . import _cabi, synth  # noqa: F401
 from ._cabi import TlsqError, load  # noqa: F401
 
-__all__ = ["rpca", "rpca_ga", "lowrankfilter", "hankel", "unhankel", "SVD", "TlsqError", "get_handle",
+__all__ = ["rpca", "rpca_ga", "lowrankfilter", "hankel", "unhankel", "rtls", "tls", "SVD", "TlsqError", "get_handle",
            "init_distributed", "launch_count", "gram", "eigh", "set_profiling", "get_profile", "PHASES"]
 
 
@@ -280,13 +280,8 @@ def lowrankfilter(y, n: Optional[int] = None, *, sv: int = 0, lag: int = 1, tol:
     rho = kwargs.pop("ρ", rho)
     if svd is not None or opnorm is not None:
         raise NotImplementedError("lowrankfilter: custom svd/opnorm callables are outside the accelerated path")
-    if sv > 0:
-        raise NotImplementedError("lowrankfilter: the sv>0 plain-SSA branch (:123-125) is outside the accelerated "
-                                  "path (SURVEY.md 8f)")
     ya = _Arr(y, "y")
-    if len(ya.shape) == 2 and ya.shape[1] > 1:
-        raise NotImplementedError("lowrankfilter: multi-channel signals are outside the accelerated path "
-                                  "(SURVEY.md 8f)")
+    Dch = 1 if len(ya.shape) == 1 else int(ya.shape[1])
     Ns = ya.shape[0]
     if n is None:
         n = min(Ns // 20, 2000)                                              # :119
@@ -299,15 +294,22 @@ def lowrankfilter(y, n: Optional[int] = None, *, sv: int = 0, lag: int = 1, tol:
     flags = (_cabi.TLSQ_NONNEG_A if nonnegA else 0) | (_cabi.TLSQ_NONNEG_E if nonnegE else 0) | \
             (_cabi.TLSQ_HANKEL if hankel else 0) | (0 if nukeA else _cabi.TLSQ_NO_NUKE_A) | \
             (_cabi.TLSQ_EXACT_COST if verbose else 0)
-    yf, pyf = _empty_like(ya, (Ns,))
+    yf, pyf = _empty_like(ya, (Ns,) if len(ya.shape) == 1 else (Ns, Dch))
     svo = C.c_int64(0)
     its = C.c_int64(0)
     conv = C.c_int32(0)
     hist = np.zeros((max(int(iters), 1), 3), dtype=np.float64)
-    fn = lib.tlsq_lowrankfilter_f64_dev if ya.torch else lib.tlsq_lowrankfilter_f64
-    _cabi.check(fn(h, ya.ptr, Ns, int(n), int(lag), float(lam) if lam is not None else 0.0,
-                   int(maxrank) if maxrank is not None else 0, int(iters), float(tol), float(rho), flags, pyf,
-                   C.byref(svo), C.byref(its), C.byref(conv), C.c_void_p(hist.ctypes.data)))
+    if Dch == 1 and sv <= 0:
+        fn = lib.tlsq_lowrankfilter_f64_dev if ya.torch else lib.tlsq_lowrankfilter_f64
+        _cabi.check(fn(h, ya.ptr, Ns, int(n), int(lag), float(lam) if lam is not None else 0.0,
+                       int(maxrank) if maxrank is not None else 0, int(iters), float(tol), float(rho), flags, pyf,
+                       C.byref(svo), C.byref(its), C.byref(conv), C.c_void_p(hist.ctypes.data)))
+    else:
+        # channels (:83-90, :53-68) and / or the sv > 0 plain-SSA branch (:123-125)
+        fn = lib.tlsq_lowrankfilter_mc_f64_dev if ya.torch else lib.tlsq_lowrankfilter_mc_f64
+        _cabi.check(fn(h, ya.ptr, Ns, Dch, int(n), int(lag), int(sv), float(lam) if lam is not None else 0.0,
+                       int(maxrank) if maxrank is not None else 0, int(iters), float(tol), float(rho), flags, pyf,
+                       C.byref(svo), C.byref(its), C.byref(conv), C.c_void_p(hist.ctypes.data)))
     k = int(its.value)
     if verbose:
         for row in hist[:k]:
@@ -323,32 +325,40 @@ def lowrankfilter(y, n: Optional[int] = None, *, sv: int = 0, lag: int = 1, tol:
 
 
 def hankel(x, L: int, lag: int = 1):
-    """``X = hankel(x, L, lag=1)``: K x L trajectory matrix, K = (N-L)÷lag+1 (src/robustPCA.jl:76-92), one channel."""
+    """``X = hankel(x, L, lag=1)``: K x (L D) trajectory matrix of an N (x D) signal, K = (N-L)÷lag+1
+    (src/robustPCA.jl:76-92)."""
     xa = _Arr(np.asarray(x, dtype=np.float64) if not _is_torch(x) else x.detach().cpu().numpy(), "x")
-    if len(xa.shape) != 1:
-        raise NotImplementedError("hankel: multi-channel signals are outside the accelerated path (SURVEY.md 8f)")
     Ns = xa.shape[0]
+    D = 1 if len(xa.shape) == 1 else int(xa.shape[1])
     if L > Ns / 2:
         raise AssertionError(f"L has to be less than N/2 = {Ns / 2}")
     if lag > L:
         raise AssertionError("lag must be <= L")
     K = (Ns - L) // lag + 1
-    H = np.empty((K, L), dtype=np.float64, order="F")
-    _cabi.check(load().tlsq_hankel_f64(get_handle(None), xa.ptr, Ns, int(L), int(lag), C.c_void_p(H.ctypes.data)))
+    H = np.empty((K, L * D), dtype=np.float64, order="F")
+    if D == 1:
+        _cabi.check(load().tlsq_hankel_f64(get_handle(None), xa.ptr, Ns, int(L), int(lag), C.c_void_p(H.ctypes.data)))
+    else:
+        _cabi.check(load().tlsq_hankel_mc_f64(get_handle(None), xa.ptr, Ns, D, int(L), int(lag),
+                                              C.c_void_p(H.ctypes.data)))
     return H
 
 
 def unhankel(A, lag: int = 1, N: Optional[int] = None, D: int = 1):
     """``unhankel(A)`` / ``unhankel(A, lag, N, D=1)``: anti-diagonal averaging (src/robustPCA.jl:28-39, 53-68)."""
-    if D != 1:
-        raise NotImplementedError("unhankel: multi-channel signals are outside the accelerated path (SURVEY.md 8f)")
     Aa = _Arr(np.asarray(A, dtype=np.float64) if not _is_torch(A) else A.detach().cpu().numpy(), "A")
-    K, L = Aa.shape
+    K, LD = Aa.shape
+    L = LD // int(D)
     if N is None:
         N = L + (K - 1) * lag
-    y = np.empty(int(N), dtype=np.float64)
-    _cabi.check(load().tlsq_unhankel_f64(get_handle(None), Aa.ptr, K, L, int(lag), int(N),
-                                         C.c_void_p(y.ctypes.data)))
+    if D == 1:
+        y = np.empty(int(N), dtype=np.float64)
+        _cabi.check(load().tlsq_unhankel_f64(get_handle(None), Aa.ptr, K, L, int(lag), int(N),
+                                             C.c_void_p(y.ctypes.data)))
+    else:
+        y = np.empty((int(N), int(D)), dtype=np.float64, order="F")
+        _cabi.check(load().tlsq_unhankel_mc_f64(get_handle(None), Aa.ptr, K, L, int(lag), int(N), int(D),
+                                                C.c_void_p(y.ctypes.data)))
     return y
 
 
@@ -407,6 +417,35 @@ def rpca_ga(X, r: Optional[int] = None, U=None, *, verbose: bool = False, tol: f
 # ------------------------------------------------------------------------------------------------------
 # building blocks (tests / profiling)
 # ------------------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------------------
+# rtls: the in-package caller of rpca that consumes the returned SVD (src/TotalLeastSquares.jl:48-69, 152-156)
+# ----------------------------------------------------------------------------------------------------------
+def _tls_from_v(V, n: int):
+    """tls!(s::SVD, n): x = -V21 / V22 with V = s.V (src/TotalLeastSquares.jl:65-69).  Tiny host-side solve."""
+    V = np.asarray(V.cpu().numpy() if _is_torch(V) else V)
+    V21, V22 = V[:n, n:], V[n:, n:]
+    return -np.linalg.solve(V22.T, V21.T).T                        # V21 / V22  (right division)
+
+
+def tls(A, y):
+    """``x = tls(A, y)``: total least squares by the SVD of [A y] (src/TotalLeastSquares.jl:48-55); host NumPy -- not
+    part of the accelerated path, provided because rtls (below) is defined through it."""
+    A = np.asarray(A, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(A.shape[0], -1)
+    _, _, Vt = np.linalg.svd(np.hstack([A, y]), full_matrices=False)
+    return _tls_from_v(Vt.T, A.shape[1])
+
+
+def rtls(A, y, **kwargs):
+    """``x = rtls(A, y; kwargs...)``: robust TLS = rpca([A y]; nukeA=false, kwargs...) on the GPU followed by tls! on
+    the returned SVD (src/TotalLeastSquares.jl:152-156)."""
+    A = np.asarray(A, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(A.shape[0], -1)
+    kwargs.setdefault("nukeA", False)
+    _, _, s, _ = rpca(np.asfortranarray(np.hstack([A, y])), **kwargs)
+    return _tls_from_v(np.asarray(s.Vt).T, A.shape[1])
+
+
 def gram(X):
     """G = X'X through the DMMA SYRK kernel (X: CUDA float64 tensor, column-major)."""
     import torch

@@ -20,6 +20,8 @@ _RPCA_ARGS = [vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.
               vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i32p, vp]
 _LRF_ARGS = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_double, C.c_double,
              C.c_uint32, vp, c_i64p, c_i64p, c_i32p, vp]
+_LRF_MC_ARGS = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64,
+                C.c_double, C.c_double, C.c_uint32, vp, c_i64p, c_i64p, c_i32p, vp]
 _GA_ARGS = [vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_double, C.c_int64, vp, c_i64p]
 
 SIGNATURES = {
@@ -43,6 +45,10 @@ SIGNATURES = {
     "tlsq_rpca_ga_f64_dev": (C.c_int, _GA_ARGS),
     "tlsq_hankel_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, vp]),
     "tlsq_unhankel_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]),
+    "tlsq_lowrankfilter_mc_f64": (C.c_int, _LRF_MC_ARGS),
+    "tlsq_lowrankfilter_mc_f64_dev": (C.c_int, _LRF_MC_ARGS),
+    "tlsq_hankel_mc_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]),
+    "tlsq_unhankel_mc_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]),
     "tlsq_gram_f64_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),
     "tlsq_eigh_f64_dev": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
 }

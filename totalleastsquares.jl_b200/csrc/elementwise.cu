@@ -210,6 +210,105 @@ unhankel_divide_count_kernel(const double* __restrict__ sum, int64_t K, int64_t 
     }
 }
 
+// multi-channel trajectory matrix (:83-90): x is Ns x D (column-major), H is K x (L*D), H[k, l*D + d] = x[k*lag + l, d]
+__global__ void __launch_bounds__(256)
+hankel_mc_kernel(const double* __restrict__ x, int64_t Ns, int64_t D, int64_t K, int64_t L, int64_t lag,
+                 double* __restrict__ H) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t col = 0; col < L * D; ++col) {
+            const int64_t l = col / D, d = col % D;
+            H[col * K + k] = x[d * Ns + k * lag + l];
+        }
+}
+
+// general unhankel (:53-68): y[t, d] = sum of A[k, l*D + d] over k*lag + l == t, divided by max(count, 1)
+__global__ void __launch_bounds__(256)
+unhankel_mc_kernel(const double* __restrict__ A, int64_t K, int64_t L, int64_t lag, int64_t Ns, int64_t D,
+                   double* __restrict__ y) {
+    const int64_t total = Ns * D;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tt = idx % Ns, d = idx / Ns;
+        double s = 0.0;
+        int64_t cnt = 0;
+        for (int64_t l = 0; l < L; ++l) {
+            const int64_t rem = tt - l;
+            if (rem < 0) break;
+            if (rem % lag) continue;
+            const int64_t k = rem / lag;
+            if (k >= K) continue;
+            s += A[(l * D + d) * K + k];
+            ++cnt;
+        }
+        y[idx] = s / (double)(cnt > 0 ? cnt : 1);
+    }
+}
+
+// rank-sv projection A = (H V_sv) V_sv' (the sv > 0 plain-SSA branch of lowrankfilter, :123-125); thread <-> row,
+// V (n x n eigenvectors of H'H, ld n) is read through L1/L2, 16 components per sweep
+template <bool HANKEL>
+__global__ void __launch_bounds__(128)
+ssa_project_kernel(const MatSrc H, int64_t M, int64_t N, const double* __restrict__ V, int sv, double* __restrict__ A) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < M; row += (int64_t)gridDim.x * blockDim.x) {
+        for (int c0 = 0; c0 < sv; c0 += 16) {
+            double t[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = 0.0;
+            for (int64_t j = 0; j < N; ++j) {
+                const double hv = src_at<HANKEL>(H, row, j);
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c0 + c < sv) t[c] = fma(hv, __ldg(V + (int64_t)(c0 + c) * N + j), t[c]);
+            }
+            for (int64_t j = 0; j < N; ++j) {
+                double acc = c0 ? A[j * M + row] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c0 + c < sv) acc = fma(t[c], __ldg(V + (int64_t)(c0 + c) * N + j), acc);
+                A[j * M + row] = acc;
+            }
+        }
+    }
+}
+
+// soft_th(x, eps, l) = max(x - eps, l) + min(x + eps, l) - l            src/robustPCA.jl:2 (no FMA contraction)
+__device__ __forceinline__ double soft_th_level(double x, double eps, double l) {
+    return __dsub_rn(__dadd_rn(fmax(__dsub_rn(x, eps), l), fmin(__dadd_rn(x, eps), l)), l);
+}
+
+// hankel=true, second half of the iteration (thread <-> row):  A = soft_hankel(A_raw); clamp; E; Z; Y; ||Z||_F^2
+template <bool HANKEL>
+__global__ void __launch_bounds__(256)
+hankel_finish_kernel(const EpiArgs a, const double* __restrict__ mean) {
+    double zz = 0.0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.M; row += (int64_t)gridDim.x * blockDim.x) {
+        for (int64_t col = 0; col < a.N; ++col) {
+            const int64_t off = col * a.ldw + row;
+            const double d = src_at<HANKEL>(a.D, row, col);
+            const double yp = __ldg(a.Yp + off);
+            double e, w;
+            alm_ew(d, __ldg(a.Ap + off), yp, a.im, a.eps, a.nonnegE, e, w);
+            double an = soft_th_level(a.An[off], a.eps, __ldg(mean + row + col));        // soft_hankel!(A, lambda/mu) :215
+            if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;               // :218
+            const double z = __dsub_rn(__dsub_rn(d, an), e);                              // :221
+            const double yn = __dadd_rn(yp, __dmul_rn(a.mu, z));                          // :222
+            zz = fma(z, z, zz);
+            a.An[off] = an;
+            a.Yn[off] = yn;
+            if (a.Zout) a.Zout[off] = z;
+        }
+    }
+    zz = warp_sum(zz);
+    if ((threadIdx.x & 31) == 0) atomicAdd(a.zz, zz);
+}
+
+__global__ void __launch_bounds__(256)
+soft_hankel_apply_kernel(double* __restrict__ X, int64_t M, int64_t N, const double* __restrict__ mean, double eps) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < M; row += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t col = 0; col < N; ++col)
+            X[col * M + row] = soft_th_level(X[col * M + row], eps, __ldg(mean + row + col));
+}
+
 inline int stream_grid(int64_t total, int sm_count) {
     int64_t want = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count * 8;
@@ -315,6 +414,46 @@ cudaError_t launch_unhankel_factors(const double* T, int64_t ldt, const double* 
 cudaError_t launch_unhankel_divide_count(const double* sum, int64_t K, int64_t n, int64_t Ns, double* y, cudaStream_t st,
                                          int64_t* launches) {
     unhankel_divide_count_kernel<<<stream_grid(Ns, 148), 256, 0, st>>>(sum, K, n, Ns, y);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hankel_finish(const EpiArgs& a, bool hankel_src, const double* mean, int sm_count, cudaStream_t st,
+                                 int64_t* launches) {
+    const int grid = stream_grid(a.M, sm_count);
+    if (hankel_src) hankel_finish_kernel<true><<<grid, 256, 0, st>>>(a, mean);
+    else hankel_finish_kernel<false><<<grid, 256, 0, st>>>(a, mean);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_soft_hankel_apply(double* X, int64_t M, int64_t N, const double* mean, double eps, int sm_count,
+                                     cudaStream_t st, int64_t* launches) {
+    soft_hankel_apply_kernel<<<stream_grid(M, sm_count), 256, 0, st>>>(X, M, N, mean, eps);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hankel_mc(const double* x, int64_t Ns, int64_t D, int64_t K, int64_t L, int64_t lag, double* H,
+                             cudaStream_t st, int64_t* launches) {
+    hankel_mc_kernel<<<stream_grid(K, 148), 256, 0, st>>>(x, Ns, D, K, L, lag, H);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unhankel_mc(const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, int64_t D, double* y,
+                               cudaStream_t st, int64_t* launches) {
+    unhankel_mc_kernel<<<stream_grid(Ns * D, 148), 256, 0, st>>>(A, K, L, lag, Ns, D, y);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ssa_project(const MatSrc& H, bool hankel, int64_t M, int64_t N, const double* V, int sv, double* A,
+                               int sm_count, cudaStream_t st, int64_t* launches) {
+    int64_t blocks = (M + 127) / 128;
+    if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+    if (hankel) ssa_project_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(H, M, N, V, sv, A);
+    else ssa_project_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(H, M, N, V, sv, A);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -146,7 +146,9 @@ epilogue_kernel(const EpiArgs a, int ntiles) {
         __syncthreads();
 
         // ---- phase 4: clamp, residual, dual update (coalesced; D/A/Y re-read from L2) ---------------------------
-        if (rok) {
+        if (rok && a.raw_only) {
+            for (int col = ecol0; col < N; col += 16) a.An[(int64_t)col * a.ldw + row] = Wsm[col * ERS + erow];
+        } else if (rok) {
             for (int col = ecol0; col < N; col += 16) {
                 const double d = src_at<HANKEL>(a.D, row, col);
                 const int64_t off = (int64_t)col * a.ldw + row;

@@ -137,6 +137,9 @@ struct EpiArgs {
     const double* Vp;
     int svp_prev;
     double* Tn;
+    // hankel=true (:214-216): the tile epilogue only writes the raw reconstruction A' = T diag(f) V_r' into An; the
+    // anti-diagonal soft threshold, clamp, Z and Y follow in launch_hankel_finish
+    int raw_only;
 };
 cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_count, cudaStream_t st,
                             int64_t* launches);
@@ -219,11 +222,29 @@ cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N,
 cudaError_t launch_transpose(const double* in, int64_t M, int64_t N, double* out, cudaStream_t st,
                              int64_t* launches);
 
+// hankel=true branch of rpca (src/robustPCA.jl:9-21, 214-216, 234-236), single GPU, dense iterate:
+//   soft_hankel!(A, eps): every anti-diagonal is soft-thresholded towards its mean  (means from launch_unhankel)
+// finish: A = soft_th(A_raw, eps, mean[r+c]); clamp; E from (D, A_prev, Y_prev); Z = D - A - E; Y += mu Z; ||Z||_F^2
+cudaError_t launch_hankel_finish(const EpiArgs& a, bool hankel_src, const double* mean, int sm_count, cudaStream_t st,
+                                 int64_t* launches);
+// X[r,c] = soft_th(X[r,c], eps, mean[r+c]) in place (the final soft_hankel!(E, lambda/mu), :234-236)
+cudaError_t launch_soft_hankel_apply(double* X, int64_t M, int64_t N, const double* mean, double eps, int sm_count,
+                                     cudaStream_t st, int64_t* launches);
+
 // hankel / unhankel (single channel) ------------------------------------------------------------------
 cudaError_t launch_hankel(const double* x, int64_t K, int64_t L, int64_t lag, double* H, cudaStream_t st,
                           int64_t* launches);
 cudaError_t launch_unhankel(const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, double* y,
                             cudaStream_t st, int64_t* launches);
+
+// multi-channel forms (x: Ns x D column-major, H: K x (L*D) with H[k, l*D + d] = x[k*lag + l, d], :83-90, :53-68)
+cudaError_t launch_hankel_mc(const double* x, int64_t Ns, int64_t D, int64_t K, int64_t L, int64_t lag, double* H,
+                             cudaStream_t st, int64_t* launches);
+cudaError_t launch_unhankel_mc(const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, int64_t D, double* y,
+                               cudaStream_t st, int64_t* launches);
+// A = (H V_sv) V_sv' : the sv > 0 plain-SSA branch of lowrankfilter (:123-125); V = eigenvectors of H'H (ld N)
+cudaError_t launch_ssa_project(const MatSrc& H, bool hankel, int64_t M, int64_t N, const double* V, int sv, double* A,
+                               int sm_count, cudaStream_t st, int64_t* launches);
 
 // row-sharded unhankel: partial anti-diagonal sums / counts of Hankel rows [r0, r0+Kl) (sum, cnt: Ns doubles, zeroed),
 // all-reduced by the caller, then divided

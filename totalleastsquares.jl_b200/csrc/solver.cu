@@ -218,6 +218,10 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     const int nonnegE = (p.flags & TLSQ_NONNEG_E) ? 1 : 0;
     const int nukeA = (p.flags & TLSQ_NO_NUKE_A) ? 0 : 1;
     const bool exact_cost = (p.flags & TLSQ_EXACT_COST) != 0;
+    // hankel=true (:214-216, 234-236): anti-diagonal soft threshold of the iterate -- dense iterate, generic kernels
+    const bool hk = (p.flags & TLSQ_HANKEL) != 0;
+    if (hk && h->nranks > 1)
+        return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: hankel=true is not available on row-sharded problems");
 
     // global row count (for the Frobenius bracket: d = min(M_global, N))
     double Mg = (double)M;
@@ -238,12 +242,12 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // Pipeline choice: the one-pass kernel needs S (Y in place) .. 2 S of device memory, the two-kernel pipeline 3 S
     // (Y x 2 + W); on B200 the two-kernel pipeline is currently the faster one when it fits (profiles/), so the
     // one-pass kernel is taken when memory asks for it or when TLSQ_FUSED=1 forces it.
-    bool fused = !no_fact && fused_eligible(D, hankel, M, N);
+    bool fused = !no_fact && !hk && fused_eligible(D, hankel, M, N);
     if (fused && !syrk_ok && (o.A || o.E || o.U)) fused = false;   // padded leading dimension: factored outputs only
     if (fused) {
         const char* env_f = getenv("TLSQ_FUSED");
         if (env_f) fused = atoi(env_f) != 0;
-        else {
+        else if (syrk_ok) {          // (without the SYRK pipeline as the alternative the one-pass kernel always wins)
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             cudaMemPool_t pool;
@@ -258,10 +262,13 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             fused = need > free_b;
         }
     }
-    bool use_w = syrk_ok && !fused;
+    bool use_w = syrk_ok && !fused && !hk;
     // the one-pass kernel moves Y / T tiles with TMA (16-byte strides): an odd row count gets a padded leading dimension
     const int64_t ldp = fused ? M + (M & 1) : M;
     bool fact = (use_w || fused) && !no_fact;
+    DevBuf bMean;
+    double* meanbuf = nullptr;
+    if (hk) { CK(bMean.alloc((size_t)(M + N) * 8, st)); meanbuf = bMean.as<double>(); }
     DevBuf bW, bT0, bT1, bV0, bV1, bFp;
     double* Wbuf = nullptr;
     auto ensure_w = [&]() -> cudaError_t {
@@ -572,6 +579,12 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                     svpb[nxt] = svp;
                 } else if (use_w && svp <= kStreamMaxRank) {
                     CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
+                } else if (hk) {
+                    // A_raw = U_r (S_r - 1/mu) V_r' ; soft_hankel!(A, lambda/mu) ; clamp ; Z ; Y   (:205-222)
+                    ea.raw_only = 1;
+                    CK(launch_epilogue(ea, hankel, false, sms, st, L));
+                    CK(launch_unhankel(ea.An, M, N, 1, M + N - 1, meanbuf, st, L));          // anti-diagonal means
+                    CK(launch_hankel_finish(ea, hankel, meanbuf, sms, st, L));
                 } else {
                     CK(launch_epilogue(ea, hankel, false, sms, st, L));
                 }
@@ -758,8 +771,14 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // produced before A_k is copied there.
     const double* Aprev_dense = Abuf[prev_idx];
     if (o.E)
+    {
         CK(launch_compute_e(D, hankel, M, N, Aprev_dense, Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
                             st, L));
+        if (hk) {                                                                        // soft_hankel!(E, lambda/mu) :234-236
+            CK(launch_unhankel(o.E, M, N, 1, M + N - 1, meanbuf, st, L));
+            CK(launch_soft_hankel_apply(o.E, M, N, meanbuf, p.lambda / mu, sms, st, L));
+        }
+    }
     if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
     if (o.U) {
@@ -798,8 +817,6 @@ int check_rpca_args(int64_t M, int64_t N, const RpcaParams& p) {
     if (p.iters < 1) return set_err(TLSQ_ERR_ARG, "rpca: iters must be >= 1");
     if (!(p.lambda > 0.0)) return set_err(TLSQ_ERR_ARG, "rpca: lambda must be > 0");
     if (!(p.rho > 0.0)) return set_err(TLSQ_ERR_ARG, "rpca: rho must be > 0");
-    if (p.flags & TLSQ_HANKEL)
-        return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: hankel=true (soft_hankel!) is outside the accelerated path");
     return TLSQ_OK;
 }
 
@@ -918,12 +935,17 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
     // sums are taken straight from A_k = clamp(T_k V_k'); sharded runs all-reduce the Ns partial sums.
     {
         static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
-        const int64_t base = K / h->nranks, rem = K % h->nranks;
-        const int64_t r0 = h->rank * base + (h->rank < rem ? h->rank : rem);
-        const int64_t Kl = base + (h->rank < rem ? 1 : 0);
-        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && Kl >= 1 &&
-            (syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), Kl, n, Kl) ||
-             fused_eligible(MatSrc{y + r0, 1}, true, Kl, n))) {
+        // shard boundaries on multiples of 32 rows (TMA / tile friendly); the last rank takes the remainder
+        int64_t per = ((K + h->nranks - 1) / h->nranks + 31) / 32 * 32;
+        if (per * (h->nranks - 1) >= K) per = K / h->nranks;          // tiny problems: plain split
+        const int64_t r0 = per * h->rank;
+        const int64_t Kl = (h->rank == h->nranks - 1) ? K - r0 : per;
+        // the decision must be the same on every rank (collectives): test the regular shard and the last one
+        auto shard_ok = [&](int64_t rows) {
+            return rows >= 1 && (syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), rows, n, rows) ||
+                                 fused_eligible(MatSrc{y, 1}, true, rows, n));
+        };
+        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && shard_ok(per) && shard_ok(K - per * (h->nranks - 1))) {
             CKR(check_rpca_args(Kl, n, p));
             DevBuf bSum;
             CK(bSum.alloc((size_t)Ns * 8, st));
@@ -981,6 +1003,100 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
         CKR(rpca_dev(h, bH.as<double>(), K, n, p, o));
     }
     CK(launch_unhankel(o.A, K, n, lag, Ns, yf, st, &h->launches));                       // :127
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// G = X'X of a dense tall matrix (no all-reduce)
+int gram_dense(tlsq_handle* h, const double* X, int64_t M, int64_t n, double* G) {
+    cudaStream_t st = h->stream;
+    DevBuf bP;
+    if (syrk_tma_eligible(X, M, n, M)) {
+        SyrkPlan sp = syrk_plan(M, n, h->sm_count);
+        CK(bP.alloc(sp.partial_bytes, st));
+        CK(launch_syrk_tma(X, M, n, M, sp, bP.as<double>(), G, st, &h->launches));
+    } else {
+        GramPlan plan = gram_plan(M, n, h->sm_count);
+        CK(bP.alloc(plan.partial_bytes, st));
+        GramSrc gs;
+        gs.D = MatSrc{X, M}; gs.A = nullptr; gs.Y = nullptr; gs.A2 = nullptr; gs.ldw = M; gs.M = M; gs.N = n;
+        gs.im = 0.0; gs.eps = 0.0; gs.nonnegE = 0;
+        CK(launch_gram(gs, GRAM_D, false, plan, bP.as<double>(), G, st, &h->launches));
+    }
+    return TLSQ_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// lowrankfilter, general form (src/robustPCA.jl:119-128): Dch channels (y: Ns x Dch column-major) and the sv > 0
+// plain-SSA branch (:123-125).  One channel with sv <= 0 takes the implicit-Hankel path above; everything else
+// materialises the K x (n Dch) trajectory matrix (these shapes are small: the multi-channel / SSA uses of the
+// reference are test-sized) and reuses rpca_dev / the Gram + Jacobi building blocks.
+// ----------------------------------------------------------------------------------------------------------
+int lowrankfilter_general_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t Dch, int64_t n, int64_t lag,
+                              int64_t sv_ssa, RpcaParams p, double* yf, int64_t* sv, int64_t* iters_done,
+                              int32_t* converged, double* hist) {
+    if (Dch == 1 && sv_ssa <= 0)
+        return lowrankfilter_dev(h, y, Ns, n, lag, p, yf, sv, iters_done, converged, hist);
+    if (!y || !yf) return set_err(TLSQ_ERR_ARG, "lowrankfilter: y and yf are required");
+    if (Ns < 2 || n < 1 || lag < 1 || Dch < 1) return set_err(TLSQ_ERR_ARG, "lowrankfilter: bad sizes");
+    if ((double)n > (double)Ns / 2.0) return set_err(TLSQ_ERR_ARG, "L has to be less than N/2 = %g", (double)Ns / 2.0);
+    if (lag > n) return set_err(TLSQ_ERR_ARG, "lag must be <= L");
+    if (h->nranks > 1)
+        return set_err(TLSQ_ERR_UNSUPPORTED, "lowrankfilter: multi-channel / sv > 0 forms are single-GPU only");
+    cudaStream_t st = h->stream;
+    int64_t* L = &h->launches;
+    const int64_t K = (Ns - n) / lag + 1, Lc = n * Dch;
+    DevBuf bH, bA;
+    CK(bH.alloc((size_t)K * Lc * 8, st)); CK(bA.alloc((size_t)K * Lc * 8, st));
+    double* H = bH.as<double>(); double* A = bA.as<double>();
+    CK(launch_hankel_mc(y, Ns, Dch, K, n, lag, H, st, L));                                // :120
+    if (sv_ssa > 0) {
+        // s = svd(H); A = U[:, 1:sv] S[1:sv] Vt[1:sv, :]  ==  H V_sv V_sv'  (tall) or  U_sv U_sv' H  (wide)   :124-125
+        const bool tall = K >= Lc;
+        const int64_t mm = tall ? K : Lc, nn = tall ? Lc : K;
+        if (nn > kEigMaxN) return set_err(TLSQ_ERR_UNSUPPORTED, "lowrankfilter(sv>0): min(K, n D) = %lld exceeds %d",
+                                          (long long)nn, kEigMaxN);
+        int64_t svc = sv_ssa > nn ? nn : sv_ssa;
+        DevBuf bT, bG, bV, bLam, bE, bAt;
+        const double* X = H;
+        if (!tall) {
+            CK(bT.alloc((size_t)K * Lc * 8, st));
+            CK(launch_transpose(H, K, Lc, bT.as<double>(), st, L));
+            X = bT.as<double>();
+        }
+        CK(bG.alloc((size_t)nn * nn * 8, st)); CK(bV.alloc((size_t)nn * nn * 8, st)); CK(bLam.alloc((size_t)nn * 8, st));
+        CKR(gram_dense(h, X, mm, nn, bG.as<double>()));
+        CK(bE.alloc(eig_work_doubles((int)nn) * 8, st));
+        EigWork ew;
+        double* base = bE.as<double>();
+        const size_t np = (size_t)nn + 34;
+        ew.X0 = base; base += (size_t)nn * nn;
+        ew.Xo = base; base += np * nn;
+        ew.Vo = base; base += np * nn;
+        ew.lam_raw = base; base += np;
+        ew.perm = reinterpret_cast<int*>(base); base += nn;
+        ew.info = reinterpret_cast<int*>(base);
+        CK(launch_eigh(bG.as<double>(), (int)nn, nullptr, ew, bLam.as<double>(), bV.as<double>(), h->sm_count, st, L));
+        if (tall) {
+            CK(launch_ssa_project(MatSrc{X, mm}, false, mm, nn, bV.as<double>(), (int)svc, A, h->sm_count, st, L));
+        } else {
+            CK(bAt.alloc((size_t)K * Lc * 8, st));
+            CK(launch_ssa_project(MatSrc{X, mm}, false, mm, nn, bV.as<double>(), (int)svc, bAt.as<double>(), h->sm_count,
+                                  st, L));
+            CK(launch_transpose(bAt.as<double>(), Lc, K, A, st, L));
+        }
+        if (sv) *sv = svc;
+        if (iters_done) *iters_done = 0;
+        if (converged) *converged = 1;
+        CK(cudaStreamSynchronize(st));       // temporaries above are freed in stream order after this point
+    } else {
+        if (!(p.lambda > 0.0)) p.lambda = 1.0 / sqrt((double)(K > Lc ? K : Lc));           // :157
+        RpcaOut o;
+        o.A = A; o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
+        CKR(rpca_dev(h, H, K, Lc, p, o));                                                 // :122
+    }
+    if (Dch == 1) CK(launch_unhankel(A, K, n, lag, Ns, yf, st, L));                       // :127
+    else CK(launch_unhankel_mc(A, K, n, lag, Ns, Dch, yf, st, L));
     CK(cudaStreamSynchronize(st));
     return TLSQ_OK;
 }
@@ -1220,6 +1336,64 @@ int tlsq_unhankel_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, int
     CK(cudaMemcpyAsync(bA.as<double>(), A, (size_t)K * L * 8, cudaMemcpyHostToDevice, st));
     CK(launch_unhankel(bA.as<double>(), K, L, lag, Ns, by.as<double>(), st, &h->launches));
     CK(cudaMemcpyAsync(y, by.as<double>(), (size_t)Ns * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ---- general forms: channels and the sv > 0 SSA branch ----------------------------------------------------------
+int tlsq_lowrankfilter_mc_f64_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t D, int64_t n, int64_t lag,
+                                  int64_t sv_ssa, double lambda, int64_t maxrank, int64_t iters, double tol, double rho,
+                                  uint32_t flags, double* yf, int64_t* sv, int64_t* iters_done, int32_t* converged,
+                                  double* hist) {
+    CKR(use_device(h));
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    return lowrankfilter_general_dev(h, y, Ns, D, n, lag, sv_ssa, p, yf, sv, iters_done, converged, hist);
+}
+
+int tlsq_lowrankfilter_mc_f64(tlsq_handle* h, const double* y, int64_t Ns, int64_t D, int64_t n, int64_t lag,
+                              int64_t sv_ssa, double lambda, int64_t maxrank, int64_t iters, double tol, double rho,
+                              uint32_t flags, double* yf, int64_t* sv, int64_t* iters_done, int32_t* converged,
+                              double* hist) {
+    CKR(use_device(h));
+    if (!y || !yf || Ns < 1 || D < 1) return set_err(TLSQ_ERR_ARG, "lowrankfilter: y and yf are required");
+    cudaStream_t st = h->stream;
+    DevBuf by, bf;
+    CK(by.alloc((size_t)Ns * D * 8, st)); CK(bf.alloc((size_t)Ns * D * 8, st));
+    CK(cudaMemcpyAsync(by.as<double>(), y, (size_t)Ns * D * 8, cudaMemcpyHostToDevice, st));
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    CKR(lowrankfilter_general_dev(h, by.as<double>(), Ns, D, n, lag, sv_ssa, p, bf.as<double>(), sv, iters_done,
+                                  converged, hist));
+    CK(cudaMemcpyAsync(yf, bf.as<double>(), (size_t)Ns * D * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+int tlsq_hankel_mc_f64(tlsq_handle* h, const double* x, int64_t Ns, int64_t D, int64_t L, int64_t lag, double* H) {
+    CKR(use_device(h));
+    if (!x || !H || Ns < 1 || D < 1 || L < 1 || lag < 1) return set_err(TLSQ_ERR_ARG, "hankel: bad arguments");
+    if ((double)L > (double)Ns / 2.0) return set_err(TLSQ_ERR_ARG, "L has to be less than N/2 = %g", (double)Ns / 2.0);
+    if (lag > L) return set_err(TLSQ_ERR_ARG, "lag must be <= L");
+    const int64_t K = (Ns - L) / lag + 1;
+    cudaStream_t st = h->stream;
+    DevBuf bx, bH;
+    CK(bx.alloc((size_t)Ns * D * 8, st)); CK(bH.alloc((size_t)K * L * D * 8, st));
+    CK(cudaMemcpyAsync(bx.as<double>(), x, (size_t)Ns * D * 8, cudaMemcpyHostToDevice, st));
+    CK(launch_hankel_mc(bx.as<double>(), Ns, D, K, L, lag, bH.as<double>(), st, &h->launches));
+    CK(cudaMemcpyAsync(H, bH.as<double>(), (size_t)K * L * D * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+int tlsq_unhankel_mc_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, int64_t D,
+                         double* y) {
+    CKR(use_device(h));
+    if (!A || !y || K < 1 || L < 1 || lag < 1 || Ns < 1 || D < 1) return set_err(TLSQ_ERR_ARG, "unhankel: bad arguments");
+    cudaStream_t st = h->stream;
+    DevBuf bA, by;
+    CK(bA.alloc((size_t)K * L * D * 8, st)); CK(by.alloc((size_t)Ns * D * 8, st));
+    CK(cudaMemcpyAsync(bA.as<double>(), A, (size_t)K * L * D * 8, cudaMemcpyHostToDevice, st));
+    CK(launch_unhankel_mc(bA.as<double>(), K, L, lag, Ns, D, by.as<double>(), st, &h->launches));
+    CK(cudaMemcpyAsync(y, by.as<double>(), (size_t)Ns * D * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return TLSQ_OK;
 }

@@ -6,6 +6,8 @@
 #                                   -> (A, E, s::LinearAlgebra.SVD, sv::Int)        src/robustPCA.jl:156-239
 #     rpca_ga(X, r, U; verbose, tol, iters, μ) -> Q                                 src/robustPCA.jl:255-306
 #     lowrankfilter(y, n; sv, lag, tol, svd, kwargs...) -> yf                       src/robustPCA.jl:119-128
+#     hankel(x, L, lag) / unhankel(A, lag, N, D)                                    src/robustPCA.jl:76-92 / :28-68
+#     rtls(A, y; kwargs...)                                                         src/TotalLeastSquares.jl:152-156
 # Everything numerical happens behind `ccall`; this file only marshals arguments.  Julia is NOT available in the
 # build image of this repository, so this shim could not be executed there: it is kept deliberately thin and the
 # same C entry points are exercised by the Python mirror (totalleastsquares.jl_b200/__init__.py) in the test-suite.
@@ -17,7 +19,7 @@ module TotalLeastSquaresB200
 
 using LinearAlgebra
 
-export rpca, rpca_ga, lowrankfilter
+export rpca, rpca_ga, lowrankfilter, hankel, unhankel, rtls
 
 const LIB = get(ENV, "TLSQ_B200_LIB", joinpath(@__DIR__, "..", "libtlsq_b200.so"))
 
@@ -130,34 +132,73 @@ function rpca_ga(X::AbstractMatrix{T}, r = minimum(size(X)), U = nothing; verbos
 end
 
 """
-    yf = lowrankfilter(y, n = min(length(y) ÷ 20, 2000); lag = 1, tol = 1e-3, kwargs...)
+    yf = lowrankfilter(y, n = min(size(y,1) ÷ 20, 2000); sv = 0, lag = 1, tol = 1e-3, kwargs...)
 
-Single-channel signals with `sv = 0` run on the GPU with an implicit (never materialised) Hankel embedding.
+`y` may be a vector or an `N x D` matrix of channels (src/robustPCA.jl:119-128).  One channel with `sv = 0` runs with
+an implicit (never materialised) Hankel embedding; channels and the `sv > 0` plain-SSA branch (:123-125) materialise
+the trajectory matrix on the device.
 """
-function lowrankfilter(y::AbstractVector{T}, n = min(size(y, 1) ÷ 20, 2000); sv = 0, lag = 1, tol = 1e-3,
+function lowrankfilter(y::AbstractVecOrMat{T}, n = min(size(y, 1) ÷ 20, 2000); sv = 0, lag = 1, tol = 1e-3,
                        svd = LinearAlgebra.svd!, λ = nothing, maxrank = typemax(Int), iters::Int = 1000, ρ = 1.5,
                        verbose::Bool = false, nonnegA::Bool = false, nonnegE::Bool = false, hankel::Bool = false,
                        nukeA = true, kwargs...) where T
     _only_f64(y, "lowrankfilter")
-    sv <= 0 || throw(ArgumentError("lowrankfilter: the sv > 0 SSA branch is not part of the B200 path"))
-    N = length(y)
+    N, D = size(y, 1), size(y, 2)
     n <= N / 2 || throw(AssertionError("L has to be less than N/2 = $(N/2)"))       # :79
     lag <= n || throw(AssertionError("lag must be <= L"))                            # :80
-    yd = Vector{Float64}(y)
-    yf = Vector{Float64}(undef, N)
+    yd = Array{Float64}(y)
+    yf = similar(yd)
     svo, its, conv = Ref{Int64}(0), Ref{Int64}(0), Ref{Int32}(0)
     flags = (nonnegA ? TLSQ_NONNEG_A : UInt32(0)) | (nonnegE ? TLSQ_NONNEG_E : UInt32(0)) |
             (hankel ? TLSQ_HANKEL : UInt32(0)) | (nukeA ? UInt32(0) : TLSQ_NO_NUKE_A)
     mr = maxrank == typemax(Int) ? Int64(0) : Int64(maxrank)
     GC.@preserve yd yf begin
-        check(ccall((:tlsq_lowrankfilter_f64, LIB), Cint,
-                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Int64, Int64, Float64, Float64, UInt32,
-                     Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
-                    handle(), yd, N, Int64(n), Int64(lag), λ === nothing ? 0.0 : Float64(λ), mr, Int64(iters),
-                    Float64(tol), Float64(ρ), flags, yf, svo, its, conv, C_NULL))
+        check(ccall((:tlsq_lowrankfilter_mc_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Float64, Int64, Int64, Float64,
+                     Float64, UInt32, Ptr{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
+                    handle(), yd, N, Int64(D), Int64(n), Int64(lag), Int64(sv), λ === nothing ? 0.0 : Float64(λ), mr,
+                    Int64(iters), Float64(tol), Float64(ρ), flags, yf, svo, its, conv, C_NULL))
     end
     conv[] == 0 && @warn "Maximum number of iterations reached, tol: $tol"
     yf
+end
+
+"""
+    X = hankel(x, L, lag = 1)          (src/robustPCA.jl:76-92; `x` is a vector or an `N x D` matrix)
+"""
+function hankel(x::AbstractVecOrMat{Float64}, L, lag = 1)
+    N, D = size(x, 1), size(x, 2)
+    K = (N - L) ÷ lag + 1
+    X = Matrix{Float64}(undef, K, L * D)
+    xd = Array{Float64}(x)
+    GC.@preserve xd X check(ccall((:tlsq_hankel_mc_f64, LIB), Cint,
+                                  (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}),
+                                  handle(), xd, N, Int64(D), Int64(L), Int64(lag), X))     # asserts :79-80 -> ArgumentError
+    X
+end
+
+"""
+    y = unhankel(A)  /  unhankel(A, lag, N, D = 1)          (src/robustPCA.jl:28-39, 53-68)
+"""
+function unhankel(A::AbstractMatrix{Float64}, lag = 1, N = size(A, 2) + (size(A, 1) - 1) * lag, D = 1)
+    K, L = size(A, 1), size(A, 2) ÷ D
+    y = Matrix{Float64}(undef, N, D)
+    Ad = Matrix{Float64}(A)
+    GC.@preserve Ad y check(ccall((:tlsq_unhankel_mc_f64, LIB), Cint,
+                                  (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}),
+                                  handle(), Ad, K, Int64(L), Int64(lag), Int64(N), Int64(D), y))
+    D == 1 ? vec(y) : y
+end
+
+"""
+    x = rtls(A, y; kwargs...)          (src/TotalLeastSquares.jl:152-156: rpca([A y]; nukeA=false) then tls! on its SVD)
+"""
+function rtls(A::AbstractArray, y::AbstractArray; kwargs...)
+    _, _, s, _ = rpca([A y]; nukeA = false, kwargs...)
+    n = size(A, 2)
+    V21 = s.V[1:n, n+1:end]
+    V22 = s.V[n+1:end, n+1:end]
+    -V21 / V22                                                       # tls!(s, n), src/TotalLeastSquares.jl:65-69
 end
 
 end # module
