@@ -33,8 +33,19 @@ constexpr int AT = 32, AK = 64, AKS = AK + 4;
 __global__ void __launch_bounds__(256)
 atb_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int K, int na, int nb,
            const double* __restrict__ scale2, double* __restrict__ C, int ldc, int symmetric,
-           double* __restrict__ fro2, const int* __restrict__ flags, int want_conv) {
+           double* __restrict__ fro2, const int* __restrict__ flags, int want_conv,
+           const double* __restrict__ cert_f2 = nullptr, int cert_j = 0, double cert_thr = 0.0,
+           const double* __restrict__ cert_theta = nullptr) {
     if (flags && !(flags[0] == want_conv && flags[1] == 0)) return;
+    if (cert_f2) {
+        // squaring j of the count certificate: stop as soon as the bound from the chain so far already proves it
+        // (lambda_max <= f_0 u_0, u_j = 1, u_i = sqrt(f_{i+1} u_{i+1}); every CTA evaluates the same finished numbers)
+        double u = 1.0;
+        for (int j = cert_j - 1; j >= 0; --j) u = sqrt(sqrt(cert_f2[j + 1]) * u);
+        const double bound = sqrt(cert_f2[0]) * u;
+        const double thr = cert_theta ? cert_theta[0] : cert_thr;
+        if (bound < thr * (1.0 - 1e-10)) return;
+    }
     const int ti = blockIdx.x, tj = blockIdx.y;
     if (symmetric && ti > tj) return;
     __shared__ double As[AT * AKS];
@@ -297,8 +308,11 @@ fast_finish_kernel(int n, int nsq, const double* __restrict__ f2, double tau2, i
         int good = (flags[0] == 1 && flags[1] == 0) ? 1 : 0;
         if (good) {
             // lambda_max(Gd) <= f_0 * u_0,  u_k = 1, u_j = sqrt(f_{j+1} u_{j+1})
+            // (the squaring chain stops early once it has proven the count: use the part that was computed)
+            int ne = 0;
+            while (ne < nsq && f2[ne + 1] > 0.0) ++ne;
             double u = 1.0;
-            for (int j = nsq - 1; j >= 0; --j) u = sqrt(sqrt(f2[j + 1]) * u);
+            for (int j = ne - 1; j >= 0; --j) u = sqrt(sqrt(f2[j + 1]) * u);
             const double bound = sqrt(f2[0]) * u;
             // ALM step: nothing left above tau^2.  opnorm mode: nothing left above theta_1, i.e. theta_1 IS lambda_max.
             const double thr = top1 ? theta[0] : tau2;
@@ -476,7 +490,8 @@ cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFa
     double* cout = w.Cb;
     for (int j = 0; j < NSQ; ++j) {
         // C_{j+1} = (C_j / f_j)' (C_j / f_j),  f2[j+1] = ||C_{j+1}||_F^2
-        atb_kernel<<<gs, 256, 0, st>>>(cin, n, cin, n, n, n, n, w.f2 + j, cout, n, 1, w.f2 + j + 1, w.flags, 1);
+        atb_kernel<<<gs, 256, 0, st>>>(cin, n, cin, n, n, n, n, w.f2 + j, cout, n, 1, w.f2 + j + 1, w.flags, 1,
+                                       w.f2, j, tau2, top1 ? w.theta : nullptr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         double* tmp = cin; cin = cout; cout = tmp;
     }

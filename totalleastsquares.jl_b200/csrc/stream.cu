@@ -49,7 +49,10 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
     }
     __syncthreads();
     double zz = 0.0;
-    constexpr int UB = 4;                      // columns whose loads are issued together
+#ifndef TLSQ_STREAM_UB
+#define TLSQ_STREAM_UB 4
+#endif
+    constexpr int UB = TLSQ_STREAM_UB;         // columns whose loads are issued together
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.M;
          row += (int64_t)gridDim.x * blockDim.x) {
         // ---- T[row, :] = f .* (W[row, :] V_r): one streaming read of the materialised SVT input ----------------
