@@ -34,6 +34,7 @@ import scipy.linalg as sla
 
 __all__ = [
     "soft_th", "soft_th_level", "soft_hankel", "ishankel", "hankel", "unhankel", "lowrankfilter",
+    "entrywise_trimmed_mean", "entrywise_median",
     "rpca", "rpca_ga", "rpca_ga_1", "mu_mean", "SVD", "RpcaResult",
 ]
 
@@ -289,6 +290,29 @@ def mu_mean(s, w, U, exact_order=True):
         ws = float(np.sum(w))
         s[:] = U @ w
     s /= ws
+    return s
+
+
+def entrywise_trimmed_mean(s, w, U, P=0.1):
+    """src/robustPCA.jl:323-333: per row, drop a fraction P of the sorted entries on each side, then the w-weighted
+    mean of the rest.  range = (1 + floor(P N)) : floor((1 - P) N)  (1-based, inclusive)."""
+    N = U.shape[1]
+    lo, hi = int(math.floor(P * N)), int(math.floor((1 - P) * N))            # 0-based half-open [lo, hi)
+    s[:] = 0.0
+    for j in range(U.shape[0]):
+        I = np.argsort(U[j, :], kind="stable")[lo:hi]                        # sortperm(U[j,:])[range]   :328
+        s[j] += (w[I] @ U[j, I]) / np.sum(w[I])                              # :329
+    return s
+
+
+def entrywise_median(s, w, U):
+    """src/robustPCA.jl:349-357: s[j] = sign(w[m]) U[j, m] with m the (N ÷ 2)-th entry of sortperm(w .* U[j,:])."""
+    N = U.shape[1]
+    s[:] = 0.0
+    for j in range(U.shape[0]):
+        I = np.argsort(w * U[j, :], kind="stable")
+        m = I[N // 2 - 1]                                                    # I[end ÷ 2], 1-based
+        s[j] = np.sign(w[m]) * U[j, m]
     return s
 
 

@@ -334,6 +334,26 @@ def test_rpca_ga_parity(d, N, r):
     assert np.linalg.norm(Q.T @ Q - np.eye(r)) < SQRT_EPS                 # test/runtests.jl:453
 
 
+@pytest.mark.parametrize("d,N,r", [(10, 1000, 3), (3000, 256, 3), (517, 100, 2)])
+def test_rpca_ga_robust_averages(d, N, r):
+    """rpca_ga(...; μ = entrywise_trimmed_mean / entrywise_median) (src/robustPCA.jl:323-357, test/runtests.jl:491-523):
+    per-row sorts on the GPU against the oracle restatement, same start vectors."""
+    rng = np.random.default_rng(d + N)
+    U0, S0, Vt0 = np.linalg.svd(rng.standard_normal((d, N)), full_matrices=False)
+    A = (U0[:, :r] * S0[:r]) @ Vt0[:r] + 1e-3 * rng.standard_normal((d, N))
+    A += 1000.0 * rng.standard_normal((d, N)) * (rng.random((d, N)) < 0.01)
+    A = np.asfortranarray(A)
+    q0 = np.asfortranarray(rng.standard_normal((d, r)))
+    for tag, omu in ((T.entrywise_trimmed_mean, O.entrywise_trimmed_mean), (T.entrywise_median, O.entrywise_median)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Q, info = T.rpca_ga(A, r, mu=tag, q0=q0, iters=30, return_info=True)
+            Qo, its = O.rpca_ga(A, r, q0=q0, mu=omu, exact_order=False, iters=30, return_iters=True)
+        sgn = np.sign(np.sum(Q * Qo, axis=0))
+        assert info["iters"] == its
+        assert np.abs(Q * sgn - Qo).max() < 1e-8, (tag.__name__, np.abs(Q * sgn - Qo).max())
+
+
 def test_rpca_ga_orthonormal_reference_cases():
     """test/runtests.jl:447-464 (subset), start vectors drawn by the host mirror like the reference's randn(d)"""
     rng = np.random.default_rng(1)

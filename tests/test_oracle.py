@@ -155,3 +155,27 @@ def test_max_iterations_warning():
     D, _, _, _ = golden5()
     with pytest.warns(UserWarning, match="Maximum number of iterations"):
         O.rpca(D, iters=3)
+
+
+def test_robust_averages_match_the_reference_identities():
+    """test/runtests.jl:469-488: trimmed mean with P = 0 is the weighted mean; with P = 0.1 and unit weights it is the
+    plain trimmed mean of every row (StatsBase.trim drops floor(P N) entries on each side)."""
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((10, 10))
+    s = np.zeros(10)
+    w = np.ones(10)
+    assert np.allclose(O.entrywise_trimmed_mean(s, w, U, 0).copy(), U.mean(axis=1))
+    w = rng.standard_normal(10)
+    assert np.allclose(O.entrywise_trimmed_mean(s, w, U, 0).copy(), (U * w).sum(axis=1) / w.sum())
+    w = np.ones(10)
+    m2 = O.entrywise_trimmed_mean(s, w, U, 0.1).copy()
+    for i in range(10):
+        assert np.isclose(m2[i], np.sort(U[i])[1:9].mean())
+    med = O.entrywise_median(np.zeros(10), np.ones(10), U)
+    for i in range(10):
+        assert med[i] == np.sort(U[i])[10 // 2 - 1]
+    # pluggable into rpca_ga like the reference's mu keyword (:255, :294)
+    X = rng.standard_normal((6, 200))
+    q0 = rng.standard_normal((6, 2))
+    Q = O.rpca_ga(X, 2, q0=q0, mu=O.entrywise_trimmed_mean, exact_order=False, iters=50)
+    assert np.all(np.isfinite(Q)) and np.allclose(np.linalg.norm(Q, axis=0), 1.0)

@@ -25,7 +25,8 @@ import numpy as np
 from . import _cabi, synth  # noqa: F401
 from ._cabi import TlsqError, load  # noqa: F401
 
-__all__ = ["rpca", "rpca_ga", "lowrankfilter", "hankel", "unhankel", "rtls", "tls", "SVD", "TlsqError", "get_handle",
+__all__ = ["rpca", "rpca_ga", "lowrankfilter", "hankel", "unhankel", "rtls", "tls", "entrywise_trimmed_mean",
+           "entrywise_median", "mu_mean", "SVD", "TlsqError", "get_handle",
            "init_distributed", "launch_count", "gram", "eigh", "set_profiling", "get_profile", "PHASES"]
 
 
@@ -365,6 +366,22 @@ def unhankel(A, lag: int = 1, N: Optional[int] = None, D: int = 1):
 # ------------------------------------------------------------------------------------------------------
 # rpca_ga
 # ------------------------------------------------------------------------------------------------------
+def mu_mean(*_a, **_k):
+    """Tag for the default average ``μ!`` (src/robustPCA.jl:308-316) in ``rpca_ga(...; μ=...)``."""
+    raise NotImplementedError("pass it as rpca_ga(X, r, mu=mu_mean); the average itself runs on the GPU")
+
+
+def entrywise_trimmed_mean(*_a, **_k):
+    """Tag for ``entrywise_trimmed_mean(s, w, U, P=0.1)`` (src/robustPCA.jl:323-333): ``rpca_ga(X, r, mu=entrywise_trimmed_mean)``
+    or ``mu=(entrywise_trimmed_mean, P)``; the per-row sort runs on the GPU (ga.cu)."""
+    raise NotImplementedError("pass it as rpca_ga(X, r, mu=entrywise_trimmed_mean); the average itself runs on the GPU")
+
+
+def entrywise_median(*_a, **_k):
+    """Tag for ``entrywise_median(s, w, U)`` (src/robustPCA.jl:349-357): ``rpca_ga(X, r, mu=entrywise_median)``."""
+    raise NotImplementedError("pass it as rpca_ga(X, r, mu=entrywise_median); the average itself runs on the GPU")
+
+
 def rpca_ga(X, r: Optional[int] = None, U=None, *, verbose: bool = False, tol: float = 1e-7, iters: int = 1000,
             mu=None, q0=None, return_info: bool = False, **kwargs):
     """``Q = rpca_ga(X, r=minimum(size(X)), U=similar(X); tol=1e-7, iters=1000)`` (src/robustPCA.jl:255-306).
@@ -374,9 +391,19 @@ def rpca_ga(X, r: Optional[int] = None, U=None, *, verbose: bool = False, tol: f
     buffer ``U`` is accepted for signature compatibility; the normalised copy is never formed on the GPU.
     """
     mu = kwargs.pop("μ", mu)
-    if mu is not None:
-        raise NotImplementedError("rpca_ga: custom averages (entrywise_trimmed_mean / entrywise_median) are outside "
-                                  "the accelerated path (SURVEY.md 8f)")
+    mu_kind, mu_p = 0, 0.1
+    if mu is not None and mu is not mu_mean:
+        # the reference's pluggable averages (keyword μ, :255,294) map to device kernels; other callables cannot cross
+        # the C ABI
+        if mu is entrywise_trimmed_mean or mu == "entrywise_trimmed_mean":
+            mu_kind = 1
+        elif mu is entrywise_median or mu == "entrywise_median":
+            mu_kind = 2
+        elif isinstance(mu, tuple) and mu and mu[0] is entrywise_trimmed_mean:          # (entrywise_trimmed_mean, P)
+            mu_kind, mu_p = 1, float(mu[1])
+        else:
+            raise NotImplementedError("rpca_ga: only mu!, entrywise_trimmed_mean and entrywise_median are accelerated; "
+                                      "arbitrary callables cannot cross the C ABI (no CPU fallback)")
     Xa = _Arr(X, "X")
     if len(Xa.shape) != 2:
         raise TypeError("rpca_ga: X must be a matrix")
@@ -401,8 +428,12 @@ def rpca_ga(X, r: Optional[int] = None, U=None, *, verbose: bool = False, tol: f
     h = _handle_for(Xa)
     Q, pQ = _empty_like(Xa, (d, r))
     its = (C.c_int64 * r)()
-    fn = lib.tlsq_rpca_ga_f64_dev if Xa.torch else lib.tlsq_rpca_ga_f64
-    _cabi.check(fn(h, Xa.ptr, d, N, r, q0a.ptr, float(tol), int(iters), pQ, its))
+    if mu_kind == 0:
+        fn = lib.tlsq_rpca_ga_f64_dev if Xa.torch else lib.tlsq_rpca_ga_f64
+        _cabi.check(fn(h, Xa.ptr, d, N, r, q0a.ptr, float(tol), int(iters), pQ, its))
+    else:
+        fn = lib.tlsq_rpca_ga_mu_f64_dev if Xa.torch else lib.tlsq_rpca_ga_mu_f64
+        _cabi.check(fn(h, Xa.ptr, d, N, r, q0a.ptr, float(tol), int(iters), mu_kind, mu_p, pQ, its))
     its = [int(v) for v in its]
     if verbose:
         for i, v in enumerate(its):

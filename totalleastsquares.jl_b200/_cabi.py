@@ -43,6 +43,10 @@ SIGNATURES = {
     "tlsq_lowrankfilter_f64_dev": (C.c_int, _LRF_ARGS),
     "tlsq_rpca_ga_f64": (C.c_int, _GA_ARGS),
     "tlsq_rpca_ga_f64_dev": (C.c_int, _GA_ARGS),
+    "tlsq_rpca_ga_mu_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_double, C.c_int64, C.c_int,
+                                      C.c_double, vp, c_i64p]),
+    "tlsq_rpca_ga_mu_f64_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_double, C.c_int64, C.c_int,
+                                          C.c_double, vp, c_i64p]),
     "tlsq_hankel_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, vp]),
     "tlsq_unhankel_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]),
     "tlsq_lowrankfilter_mc_f64": (C.c_int, _LRF_MC_ARGS),

@@ -189,6 +189,92 @@ inline int vec_grid(int64_t total, int sm_count) {
     return (int)want;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// Robust entry-wise averages for rpca_ga (src/robustPCA.jl:323-333 entrywise_trimmed_mean, :349-357
+// entrywise_median): per ROW j of the normalised data U[j,n] = X[j,n]/||x_n|| a sort over the N observations.
+// A block stages 32 consecutive rows x N columns in shared memory with coalesced loads (lanes along rows); every
+// warp then sorts its rows one after the other with a bitonic network on (key, index) pairs -- the index breaks ties
+// like the reference's stable sortperm.
+//   kind 1: keys = U[j,:]; s[j] = sum_{n in I} w_n U[j,n] / sum_{n in I} w_n, I = sorted[lo:hi)
+//   kind 2: keys = w .* U[j,:]; m = sorted[N/2 - 1]; s[j] = sign(w_m) U[j,m]
+// w_n = sgn_n * sqrt(n2_n) (sgn from the previous sweep's dot products, :291-293).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ga_robust_kernel(const double* __restrict__ X, int64_t d, int N, int NP2, int RT, int64_t ld,
+                 const double* __restrict__ sgn, const double* __restrict__ n2, int kind, int lo, int hi,
+                 double* __restrict__ out) {
+    extern __shared__ double smr[];
+    const int TS = RT + 1;                                // RT rows per tile (32, or 8 for long observation axes)
+    double* tile = smr;                                   // [N][RT + 1]  (padded: rows along the fast index)
+    double* wv = tile + (size_t)N * TS;                   // [N] weights
+    double* inv = wv + N;                                 // [N] 1 / ||x_n||
+    double* keys = inv + N;                               // [8 warps][NP2]
+    int* idxs = reinterpret_cast<int*>(keys + 8 * NP2);   // [8 warps][NP2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int n = tid; n < N; n += 256) {
+        const double nr = sqrt(n2[n]);
+        wv[n] = sgn[n] * nr;
+        inv[n] = nr;
+    }
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t r0 = (int64_t)blockIdx.x * RT; r0 < d; r0 += (int64_t)gridDim.x * RT) {
+        __syncthreads();
+        for (int idx = tid; idx < N * RT; idx += 256) {
+            const int n = idx / RT, r = idx % RT;
+            const int64_t row = r0 + r;
+            tile[n * TS + r] = row < d ? __ldg(X + (int64_t)n * ld + row) : 0.0;
+        }
+        __syncthreads();
+        double* kk = keys + warp * NP2;
+        int* ii = idxs + warp * NP2;
+        for (int rr = warp; rr < RT; rr += 8) {
+            const int64_t row = r0 + rr;
+            if (row >= d) break;
+            for (int n = lane; n < NP2; n += 32) {
+                double u = INF;
+                if (n < N) {
+                    u = tile[n * TS + rr] / inv[n];                              // U[j,n] = X[j,n] / Xnorms[n]   :266
+                    if (kind == 2) u = wv[n] * u;
+                }
+                kk[n] = u;
+                ii[n] = n;
+            }
+            __syncwarp();
+            for (int k = 2; k <= NP2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < NP2 / 2; t += 32) {
+                        const int a = 2 * t - (t & (j - 1));                      // lower index of the pair (bit j clear)
+                        const int b = a + j;
+                        const bool up = (a & k) == 0;
+                        const double ka = kk[a], kb = kk[b];
+                        const int ia = ii[a], ib = ii[b];
+                        const bool gt = (ka > kb) || (ka == kb && ia > ib);
+                        if (gt == up) { kk[a] = kb; kk[b] = ka; ii[a] = ib; ii[b] = ia; }
+                    }
+                    __syncwarp();
+                }
+            if (kind == 1) {
+                double num = 0.0, den = 0.0;
+                for (int p = lo + lane; p < hi; p += 32) {
+                    const double w = wv[ii[p]];
+                    num = fma(w, kk[p], num);
+                    den += w;
+                }
+                num = warp_sum(num);
+                den = warp_sum(den);
+                if (lane == 0) out[row] = num / den;
+            } else if (lane == 0) {
+                const int m = ii[N / 2 - 1];
+                const double w = wv[m];
+                const double u = tile[m * TS + rr] / inv[m];
+                out[row] = (w > 0.0 ? 1.0 : (w < 0.0 ? -1.0 : 0.0)) * u;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_ga_sweep(GaMode mode, const double* X, int64_t d, int64_t N, int64_t ld, double* vec,
@@ -248,6 +334,31 @@ cudaError_t launch_vec_scale_rsqrt(const double* v, const double* ss, int64_t d,
 cudaError_t launch_ga_deflate(double* X, int64_t d, int64_t N, int64_t ld, const double* q, const double* xs,
                               int sm_count, cudaStream_t st, int64_t* launches) {
     ga_deflate_kernel<<<vec_grid(d * N, sm_count), 256, 0, st>>>(X, d, N, ld, q, xs);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ga_robust(const double* X, int64_t d, int64_t N, int64_t ld, const double* sgn, const double* n2,
+                             int kind, double P, double* out, int sm_count, cudaStream_t st, int64_t* launches) {
+    int np2 = 2;
+    while (np2 < N) np2 <<= 1;
+    int rt = 32;
+    auto need = [&](int rows) {
+        return ((size_t)N * (rows + 1) + 2 * (size_t)N + 8 * (size_t)np2) * sizeof(double) + 8 * (size_t)np2 * sizeof(int);
+    };
+    if (need(rt) > (size_t)220 * 1024) rt = 8;
+    const size_t smem = need(rt);
+    if (smem > (size_t)220 * 1024) return cudaErrorInvalidValue;          // N > ~1024 observations
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(ga_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    const int lo = (int)floor(P * (double)N), hi = (int)floor((1.0 - P) * (double)N);      // :325
+    int64_t blocks = (d + rt - 1) / rt;
+    if (blocks > (int64_t)sm_count * 2) blocks = (int64_t)sm_count * 2;
+    ga_robust_kernel<<<(unsigned)blocks, 256, smem, st>>>(X, d, (int)N, np2, rt, ld, sgn, n2, kind, lo, hi, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -271,6 +271,10 @@ enum GaMode : int {
 cudaError_t launch_ga_sweep(GaMode mode, const double* X, int64_t d, int64_t N, int64_t ld, double* vec,
                             const double* s, const double* sumw, double* t, int sm_count, cudaStream_t st,
                             int64_t* launches);
+// robust entry-wise averages (:323-333, :349-357): out[j] (length d) from a per-row sort over the N observations;
+// kind 1 = trimmed mean (fraction P dropped on each side), 2 = median.  N is limited by shared memory (~600).
+cudaError_t launch_ga_robust(const double* X, int64_t d, int64_t N, int64_t ld, const double* sgn, const double* n2,
+                             int kind, double P, double* out, int sm_count, cudaStream_t st, int64_t* launches);
 // s[n] = sign(t[n]) (0 if norms[n]==0), sumw = sum_n s[n]*norms[n]            (:292, :310-312)
 cudaError_t launch_ga_signs(const double* t, const double* norms2, int64_t N, double* s, double* sumw,
                             cudaStream_t st, int64_t* launches);

@@ -377,7 +377,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     double* sqA = bSq.as<double>();
     double* sqB = sqA + (size_t)n * n;
     double* sqf = sqB + (size_t)n * n;         // 16 f2 + 2 bounds
-    double prev_fro = 1.0e300;
+    double prev_fro = 1.0e300, prev_prev_fro = 1.0e300;
 
     // ---- setup (:174-185) --------------------------------------------------------------------------------
     CK(cudaMemsetAsync(dscal, 0, 16 * 8, st));
@@ -506,7 +506,18 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             }
         }
         // will the Frobenius bracket [fro/sqrt(d), fro] probably straddle tol?  (fro shrinks by < 8x per iteration)
-        const bool want_z = (use_w || fused) && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
+        bool want_z = (use_w || fused) && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
+        if (fused) {
+            // One-pass pipeline.  With two Y buffers nothing is predicted: the normal pass runs, and only when the
+            // Frobenius bracket cannot decide is Z'Z formed after the fact from (Y_{k-1}, T_{k-1}, T_k).  With Y in
+            // place Y_{k-1} is gone after the pass, so iterations that may need ||Z||_2 run in two phases; the
+            // prediction extrapolates the last observed decay (4x safety) instead of assuming a fixed 8x.
+            if (!inplace_y) want_z = false;
+            else if (!exact_cost && p.tol > 0.0 && prev_prev_fro < 1.0e299) {
+                const double ratio = fmin(prev_fro / prev_prev_fro, 1.0);
+                want_z = prev_fro * ratio < 4.0 * sqrt(dmin) * p.tol;
+            }
+        }
         if (fused && (svp > kFusedMaxRank || svpb[cur] > kFusedMaxRank)) {
             // rank estimate beyond the fused kernel: materialise W_k once and continue on the streaming pipeline
             if (ldp != M || inplace_y || !syrk_ok)
@@ -619,6 +630,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             else if (fro / sqrt(dmin) >= p.tol) converged = false;
             else need_exact = true;
         }
+        prev_prev_fro = prev_fro;
         prev_fro = fro;
         if (need_exact && inplace_y && !z_gram_ready) {
             // Y was updated in place and the bracket was not predicted: Z_k cannot be rebuilt.  Only the upper bound
@@ -860,7 +872,7 @@ int rpca_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, const RpcaPa
 // Grassmann averages core (device pointers)
 // ----------------------------------------------------------------------------------------------------------
 int rpca_ga_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0, double tol,
-                int64_t iters, double* Q, int64_t* iters_done) {
+                int64_t iters, double* Q, int64_t* iters_done, int mu_kind = 0, double mu_p = 0.1) {
     if (d < 1 || N < 1 || r < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: empty problem");
     if (!X || !q0 || !Q) return set_err(TLSQ_ERR_ARG, "rpca_ga: X, q0 and Q are required");
     if (iters < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: iters must be >= 1");
@@ -894,9 +906,17 @@ int rpca_ga_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r
         for (int64_t it = 1; it <= iters; ++it) {                                        // :290
             CK(launch_ga_signs(t, n2, N, s, sc, st, L));
             CK(cudaMemsetAsync(t, 0, (size_t)(N + 1) * 8, st));
-            {
+            if (mu_kind == 0) {
                 Phase ph(h, TLSQ_PHASE_GA_SWEEP);
                 CK(launch_ga_sweep(GA_PASS, Xw, d, N, d, mu, s, sc, t, sms, st, L));     // :291-294 in one sweep
+            } else {
+                // robust entry-wise average (:323-333 / :349-357): a per-row sort over the observations (rows are local
+                // to a shard), then ||mu||^2 and the dot products of the NEXT iteration with q = mu/||mu|| -- the sign
+                // of u_n'q equals the sign of x_n'mu, so the dots are taken with mu directly
+                Phase ph(h, TLSQ_PHASE_GA_SWEEP);
+                CK(launch_ga_robust(Xw, d, N, d, s, n2, mu_kind, mu_p, mu, sms, st, L));
+                CK(launch_vec_sumsq(mu, d, t + N, sms, st, L));
+                CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, mu, nullptr, nullptr, t, sms, st, L));
             }
             CKR(allreduce(h, t, (size_t)(N + 1), kNcclSum));
             CK(cudaMemsetAsync(sc + 2, 0, 8, st));
@@ -1305,6 +1325,31 @@ int tlsq_rpca_ga_f64(tlsq_handle* h, const double* X, int64_t d, int64_t N, int6
     CK(cudaMemcpyAsync(bX.as<double>(), X, (size_t)d * N * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(bq0.as<double>(), q0, (size_t)d * r * 8, cudaMemcpyHostToDevice, st));
     CKR(rpca_ga_dev(h, bX.as<double>(), d, N, r, bq0.as<double>(), tol, iters, bQ.as<double>(), iters_done));
+    CK(cudaMemcpyAsync(Q, bQ.as<double>(), (size_t)d * r * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+int tlsq_rpca_ga_mu_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0,
+                            double tol, int64_t iters, int mu_kind, double mu_p, double* Q, int64_t* iters_done) {
+    CKR(use_device(h));
+    if (mu_kind < 0 || mu_kind > 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: mu_kind must be 0 (mean), 1 (trimmed mean) or 2 (median)");
+    if (mu_kind && N > 1024) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most 1024 observations");
+    return rpca_ga_dev(h, X, d, N, r, q0, tol, iters, Q, iters_done, mu_kind, mu_p);
+}
+
+int tlsq_rpca_ga_mu_f64(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0, double tol,
+                        int64_t iters, int mu_kind, double mu_p, double* Q, int64_t* iters_done) {
+    CKR(use_device(h));
+    if (!X || !q0 || !Q || d < 1 || N < 1 || r < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: bad arguments");
+    if (mu_kind < 0 || mu_kind > 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: mu_kind must be 0 (mean), 1 (trimmed mean) or 2 (median)");
+    if (mu_kind && N > 1024) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most 1024 observations");
+    cudaStream_t st = h->stream;
+    DevBuf bX, bq0, bQ;
+    CK(bX.alloc((size_t)d * N * 8, st)); CK(bq0.alloc((size_t)d * r * 8, st)); CK(bQ.alloc((size_t)d * r * 8, st));
+    CK(cudaMemcpyAsync(bX.as<double>(), X, (size_t)d * N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(bq0.as<double>(), q0, (size_t)d * r * 8, cudaMemcpyHostToDevice, st));
+    CKR(rpca_ga_dev(h, bX.as<double>(), d, N, r, bq0.as<double>(), tol, iters, bQ.as<double>(), iters_done, mu_kind, mu_p));
     CK(cudaMemcpyAsync(Q, bQ.as<double>(), (size_t)d * r * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return TLSQ_OK;

@@ -19,7 +19,7 @@ module TotalLeastSquaresB200
 
 using LinearAlgebra
 
-export rpca, rpca_ga, lowrankfilter, hankel, unhankel, rtls
+export rpca, rpca_ga, lowrankfilter, hankel, unhankel, rtls, entrywise_trimmed_mean, entrywise_median
 
 const LIB = get(ENV, "TLSQ_B200_LIB", joinpath(@__DIR__, "..", "libtlsq_b200.so"))
 
@@ -103,16 +103,30 @@ function rpca(D::AbstractMatrix{T};
 end
 
 """
-    Q = rpca_ga(X, r = minimum(size(X)), U = similar(X); verbose = false, tol = 1e-7, iters = 1000)
+    entrywise_trimmed_mean / entrywise_median
+
+Tags for the reference's robust averages (src/robustPCA.jl:323-333, :349-357) in `rpca_ga(...; μ = ...)`; the per-row
+sorts run on the GPU.  `μ = (entrywise_trimmed_mean, P)` selects a trimming fraction other than 0.1.
+"""
+entrywise_trimmed_mean(args...) = error("pass it as rpca_ga(X, r; μ = entrywise_trimmed_mean)")
+entrywise_median(args...) = error("pass it as rpca_ga(X, r; μ = entrywise_median)")
+
+"""
+    Q = rpca_ga(X, r = minimum(size(X)), U = similar(X); verbose = false, tol = 1e-7, iters = 1000, μ = μ!)
 
 The start vector of every component is drawn here with `randn(d)` so the global RNG is consumed exactly like the
 reference does (src/robustPCA.jl:286).  `U` is accepted for signature compatibility (the normalised copy is never
-formed on the GPU).  Custom averages `μ` are not supported by the accelerated path.
+formed on the GPU).  `μ` may be `nothing` (the default weighted mean `μ!`), `entrywise_trimmed_mean`,
+`(entrywise_trimmed_mean, P)` or `entrywise_median`; other callables cannot cross the C ABI.
 """
 function rpca_ga(X::AbstractMatrix{T}, r = minimum(size(X)), U = nothing; verbose = false, tol = 1e-7,
                  iters::Int = 1000, μ = nothing, kwargs...) where T
     _only_f64(X, "rpca_ga")
-    μ === nothing || throw(ArgumentError("rpca_ga: custom averages are not supported by the B200 path"))
+    kind, P = μ === nothing ? (0, 0.1) :
+              μ === entrywise_trimmed_mean ? (1, 0.1) :
+              μ === entrywise_median ? (2, 0.1) :
+              (μ isa Tuple && μ[1] === entrywise_trimmed_mean) ? (1, Float64(μ[2])) :
+              throw(ArgumentError("rpca_ga: only μ!, entrywise_trimmed_mean and entrywise_median are supported by the B200 path"))
     Xd = Matrix{Float64}(X)
     d, N = size(Xd)
     q0 = Matrix{Float64}(undef, d, r)
@@ -122,9 +136,10 @@ function rpca_ga(X::AbstractMatrix{T}, r = minimum(size(X)), U = nothing; verbos
     Q = Matrix{Float64}(undef, d, r)
     its = Vector{Int64}(undef, r)
     GC.@preserve Xd q0 Q its begin
-        check(ccall((:tlsq_rpca_ga_f64, LIB), Cint,
-                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Float64, Int64, Ptr{Float64}, Ptr{Int64}),
-                    handle(), Xd, d, N, Int64(r), q0, Float64(tol), Int64(iters), Q, its))
+        check(ccall((:tlsq_rpca_ga_mu_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Float64, Int64, Cint, Float64,
+                     Ptr{Float64}, Ptr{Int64}),
+                    handle(), Xd, d, N, Int64(r), q0, Float64(tol), Int64(iters), Cint(kind), P, Q, its))
     end
     verbose && foreach(i -> @info("Component $i converged after $(its[i]) iterations"), 1:r)
     any(>=(iters), its) && @warn "Reached maximum number of iterations"   # :303
