@@ -29,7 +29,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram read+write per launch of alm_fused_kernel from `ncu --set full` (profiles/), keyed by (rows per GPU, columns)
-FUSED_TRAFFIC_GB = {}
+FUSED_TRAFFIC_GB = {(1_000_000, 256): 6.32}
+# same for syrk_tma_kernel (profiles/r01_ncu_full_two_kernel_path.md: 2.90 GB read + 0.01 GB written for S = 2.05 GB)
+SYRK_TRAFFIC_GB = {(1_000_000, 256): 2.91}
+# and for the two streaming-epilogue kernels together (profiles/r01_ncu_full_stream_split.md)
+STREAM_TRAFFIC_GB = {(1_000_000, 256): 10.45}
 
 FP64_TENSOR_PEAK_TFLOPS = 37.1      # measured on this pool's B200 (tools/microbench.cu -> profiles/r01_microbench_fp64_hbm.log)
 
@@ -340,9 +344,13 @@ def run_b200(args, w, rank, world, local_rank):
             line["roofline"] = {"kernel": "syrk_tma_kernel (DMMA SYRK of the SVT input)", "bound": "tensor",
                                 "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                                 "frac": ach / FP64_TENSOR_PEAK_TFLOPS, "peak_source": peak_src64,
-                                "traffic": None, "avg_launch_ms": t_gram * 1e3}
+                                "algorithmic_flops": "M*N*(N+1) (SYRK count, SURVEY.md 8d)",
+                                "traffic": SYRK_TRAFFIC_GB.get((m, N)),
+                                "traffic_unit": "GB per launch (dram read+write, ncu --set full, profiles/)",
+                                "avg_launch_ms": t_gram * 1e3}
             t_epi = e_ms / max(e_n, 1) * 1e-3
-            line["roofline_epilogue"] = {"kernel": "alm_stream_kernel", "bound": "hbm",
+            line["roofline_epilogue"] = {"kernel": "alm_stream_kernel<PH=1> + <PH=2> (T projection, element-wise pass)",
+                                         "bound": "hbm", "traffic": STREAM_TRAFFIC_GB.get((m, N)),
                                          "achieved": 6 * S / t_epi * 1e-9 if t_epi > 0 else 0.0, "peak": hbm,
                                          "unit": "GB/s", "frac": (6 * S / t_epi * 1e-9) / hbm if t_epi > 0 else 0.0,
                                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
