@@ -217,6 +217,148 @@ jacobi_cluster_kernel(const double* __restrict__ X0, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Cluster engine, hierarchical tournament (default).  Every CTA holds two HALF-BLOCKS of spc columns (top / bottom).
+// One sweep = 2C-1 outer rounds; in an outer round a CTA rotates all spc x spc cross pairs of its two half-blocks in
+// spc inner rounds (pair (T[w], B[(w+r) % spc]) on warp w, in place in shared memory, __syncthreads between rounds),
+// then the half-blocks move one position of the circle method (top[0] fixed, top[c] -> top[c+1], top[C-1] -> bot[C-1],
+// bot[c] -> bot[c-1], bot[0] -> top[1]) through DSMEM and the cluster synchronises ONCE.  The pairs inside a
+// half-block are rotated in the first outer round of every sweep.  Every column pair is visited exactly once per
+// sweep like in the flat tournament, but with 2C-1 = 31 cluster barriers per sweep instead of 255 (n = 256).
+// ---------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256)
+jacobi_cluster_block_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n, int spc,
+                            double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
+                            int* __restrict__ info, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;      // fast path succeeded: nothing to do (uniform over the cluster)
+    constexpr int LEN = 32 * E;
+    extern __shared__ double smem[];
+    __shared__ int counters[64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int c = (int)cluster.block_rank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot_doubles = 2 * LEN;               // [X part | V part]
+    const int buf_doubles = 2 * spc * slot_doubles; // slots 0..spc-1 = top half-block, spc..2spc-1 = bottom
+    double* buf0 = smem;
+    double* buf1 = smem + buf_doubles;
+    if (threadIdx.x < 64) counters[threadIdx.x] = 0;
+
+    // initial load: column j -> CTA j / (2 spc), slot j % (2 spc).  Columns >= n are zero dummies.
+    for (int sl = warp; sl < 2 * spc; sl += 8) {
+        const int j = c * 2 * spc + sl;
+        double* dst = buf0 + sl * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane + 32 * e;
+            double xv = 0.0, vv = 0.0;
+            if (j < n && i < n) {
+                xv = X0[(int64_t)j * n + i];
+                vv = V0 ? V0[(int64_t)j * n + i] : (i == j ? 1.0 : 0.0);
+            }
+            dst[i] = xv;
+            dst[LEN + i] = vv;
+        }
+    }
+    cluster.sync();
+
+    int* counters0 = cluster.map_shared_rank(counters, 0);
+    double* cur = buf0;
+    double* nxt = buf1;
+    const int spe = spc + (spc & 1);                // even size of the in-block tournament
+    const int outer = 2 * C - 1;
+    int sweep = 0;
+
+    auto rotate_slots = [&](int sa, int sb) -> bool {
+        double xp[E], xq[E], vp[E], vq[E];
+        double* pa = cur + sa * slot_doubles;
+        double* pb = cur + sb * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            xp[e] = pa[lane + 32 * e];
+            vp[e] = pa[LEN + lane + 32 * e];
+            xq[e] = pb[lane + 32 * e];
+            vq[e] = pb[LEN + lane + 32 * e];
+        }
+        if (!jacobi_rotate<E>(xp, xq, vp, vq, tol)) return false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            pa[lane + 32 * e] = xp[e];
+            pa[LEN + lane + 32 * e] = vp[e];
+            pb[lane + 32 * e] = xq[e];
+            pb[LEN + lane + 32 * e] = vq[e];
+        }
+        return true;
+    };
+
+    for (; sweep < max_sweeps; ++sweep) {
+        bool rotated = false;
+        for (int orow = 0; orow < outer; ++orow) {
+            if (orow == 0 && spc > 1) {
+                // pairs inside the two half-blocks: circle method on spe columns, warps [0, spe/2) on top, next on bottom
+                for (int r = 0; r < spe - 1; ++r) {
+                    const int half = warp / (spe / 2), pi = warp % (spe / 2);
+                    if (half < 2) {
+                        int p, q;
+                        if (pi == 0) { p = spe - 1; q = r; }
+                        else { p = (r + pi) % (spe - 1); q = (r - pi + (spe - 1)) % (spe - 1); }
+                        if (p < spc && q < spc) rotated |= rotate_slots(half * spc + p, half * spc + q);
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int r = 0; r < spc; ++r) {
+                if (warp < spc) rotated |= rotate_slots(warp, spc + (warp + r) % spc);
+                __syncthreads();
+            }
+            // move the half-blocks (every column is copied into the next buffer of its destination CTA)
+            for (int sl = warp; sl < 2 * spc; sl += 8) {
+                const int top = sl < spc ? 1 : 0, l = top ? sl : sl - spc;
+                int dc, dtop;
+                if (C == 1) { dc = 0; dtop = top; }
+                else if (top) {
+                    if (c == 0) { dc = 0; dtop = 1; }
+                    else if (c == C - 1) { dc = C - 1; dtop = 0; }
+                    else { dc = c + 1; dtop = 1; }
+                } else {
+                    if (c == 0) { dc = 1; dtop = 1; }
+                    else { dc = c - 1; dtop = 0; }
+                }
+                const double* src = cur + sl * slot_doubles;
+                double* base = (dc == c) ? nxt : cluster.map_shared_rank(nxt, dc);
+                double* dst = base + ((dtop ? 0 : spc) + l) * slot_doubles;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    dst[lane + 32 * e] = src[lane + 32 * e];
+                    dst[LEN + lane + 32 * e] = src[LEN + lane + 32 * e];
+                }
+            }
+            cluster.sync();
+            double* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        if (rotated && lane == 0) atomicAdd(counters0 + sweep, 1);
+        cluster.sync();
+        const int cnt = *((volatile int*)(counters0 + sweep));
+        if (cnt == 0) { ++sweep; break; }
+    }
+    cluster.sync();   // nobody may exit while a peer still reads counters0 / writes DSMEM
+
+    for (int sl = warp; sl < 2 * spc; sl += 8) {   // write back (order is irrelevant; eig_post sorts)
+        const int j = c * 2 * spc + sl;
+        const double* src = cur + sl * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane + 32 * e;
+            if (i < n) {
+                Xo[(int64_t)j * n + i] = src[i];
+                Vo[(int64_t)j * n + i] = src[LEN + i];
+            }
+        }
+    }
+    if (c == 0 && threadIdx.x == 0) info[0] = sweep;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Global-memory engine (cooperative launch): columns live in Xo / Vo (L2 resident), one warp per pair.
 // ---------------------------------------------------------------------------------------------------
 template <int E>
@@ -367,7 +509,8 @@ cudaError_t launch_cluster(const double* X0, const double* V0, int n, int C, int
                            double* Xo, double* Vo, int* info, const int* run_flag, cudaStream_t st) {
     constexpr int LEN = 32 * E;
     const size_t smem = (size_t)2 * 2 * spc * 2 * LEN * sizeof(double);
-    auto kern = jacobi_cluster_kernel<E>;
+    static const bool flat = getenv("TLSQ_JACOBI_FLAT") != nullptr;      // comparison hook: one cluster barrier per round
+    auto kern = flat ? jacobi_cluster_kernel<E> : jacobi_cluster_block_kernel<E>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (C > 8) {
