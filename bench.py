@@ -30,10 +30,10 @@ sys.path.insert(0, ROOT)
 
 # dram read+write per launch of alm_fused_kernel from `ncu --set full` (profiles/), keyed by (rows per GPU, columns)
 FUSED_TRAFFIC_GB = {(1_000_000, 256): 6.32}
-# same for syrk_tma_kernel (profiles/r01_ncu_full_two_kernel_path.md: 2.90 GB read + 0.01 GB written for S = 2.05 GB)
-SYRK_TRAFFIC_GB = {(1_000_000, 256): 2.91}
-# and for the two streaming-epilogue kernels together (profiles/r01_ncu_full_stream_split.md)
-STREAM_TRAFFIC_GB = {(1_000_000, 256): 10.45}
+# same for syrk_tma_kernel (profiles/r01_ncu_full_final.md: 3.57 GB read + 0.01 GB written for S = 2.05 GB)
+SYRK_TRAFFIC_GB = {(1_000_000, 256): 3.58}
+# and for the two streaming-epilogue kernels together (profiles/r01_ncu_full_stream_split.md: 2.14 + 8.27 GB at RP = 12)
+STREAM_TRAFFIC_GB = {(1_000_000, 256): 10.41}
 
 FP64_TENSOR_PEAK_TFLOPS = 37.1      # measured on this pool's B200 (tools/microbench.cu -> profiles/r01_microbench_fp64_hbm.log)
 

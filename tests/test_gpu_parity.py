@@ -269,7 +269,7 @@ def test_fused_pipeline_equals_two_kernel_pipeline(monkeypatch):
     monkeypatch.setenv("TLSQ_FUSED", "1")
     assert i1["iters"] == i2["iters"] and sv1 == sv2
     assert relF(A1, A2) < 1e-12 and relF(E1, E2) < 1e-12 and np.array_equal(E1 != 0, E2 != 0)
-    assert np.allclose(s1.S, s2.S, rtol=0, atol=1e-12 * s2.S[0])
+    assert np.allclose(s1.S, s2.S, rtol=0, atol=1e-9 * s2.S[0])      # Gram route: the tail of S carries eps*S[0]^2/S[i]
     y, yn = T.synth.sinusoid_np(12255, seed=2, noise=0.05)                # K = 12000 Hankel rows x 256
     yo = O.lowrankfilter(yn, 256)
     yf, info = T.lowrankfilter(yn, 256, return_info=True)
