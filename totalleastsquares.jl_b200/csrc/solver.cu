@@ -239,30 +239,53 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     // then neither read nor written inside the loop; it is materialised only for the outputs, or for good (one-way
     // switch to the dense representation) if the rank estimate ever exceeds 32.
     static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
-    // Pipeline choice: the one-pass kernel needs S (Y in place) .. 2 S of device memory, the two-kernel pipeline 3 S
-    // (Y x 2 + W); on B200 the two-kernel pipeline is currently the faster one when it fits (profiles/), so the
-    // one-pass kernel is taken when memory asks for it or when TLSQ_FUSED=1 forces it.
-    bool fused = !no_fact && !hk && fused_eligible(D, hankel, M, N);
-    if (fused && !syrk_ok && (o.A || o.E || o.U)) fused = false;   // padded leading dimension: factored outputs only
-    if (fused) {
-        const char* env_f = getenv("TLSQ_FUSED");
-        if (env_f) fused = atoi(env_f) != 0;
-        else if (syrk_ok) {          // (without the SYRK pipeline as the alternative the one-pass kernel always wins)
-            size_t free_b = 0, total_b = 0;
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
-                uint64_t reserved = 0, used = 0;
-                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-                if (reserved > used) free_b += (size_t)(reserved - used);
-            }
-            // two-kernel pipeline: Y x 2, W and (late iterations) Z  ->  4 S + workspace
-            const size_t need = 4 * mn * 8 + mn * 8 / 4 + ((size_t)4 << 30);
-            fused = need > free_b;
+    // Pipeline choice: the one-pass kernel needs S (Y in place) .. 2 S of device memory, the two-kernel pipeline up to
+    // 4 S (Y x 2, W, Z); on B200 the two-kernel pipeline is currently the faster one when it fits (profiles/), so the
+    // one-pass kernel is taken when memory asks for it, when the two-kernel pipeline is not available (odd row count
+    // of an implicit Hankel shard) or when TLSQ_FUSED=1 forces it.  The choice MUST be the same on every rank of a
+    // sharded solve (the pipelines issue different collectives), so the local capabilities and wishes are summed over
+    // the ranks first.
+    auto device_free_bytes = [&]() -> size_t {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+            uint64_t reserved = 0, used = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            if (reserved > used) free_b += (size_t)(reserved - used);
         }
+        return free_b;
+    };
+    const size_t free_b = device_free_bytes();
+    const size_t ws_bytes = (size_t)4 << 30;
+    bool can_fused = !no_fact && !hk && fused_eligible(D, hankel, M, N);
+    if (can_fused && !syrk_ok && (o.A || o.E || o.U)) can_fused = false;   // padded leading dimension: factored outputs only
+    const bool can_legacy = syrk_ok && !hk;
+    const bool wants_fused = 4 * mn * 8 + mn * 2 + ws_bytes > free_b;      // Y x 2, W, Z (+ factors) do not fit
+    const bool wants_inplace = 2 * mn * 8 + mn * 2 + ws_bytes > free_b;    // not even two copies of Y fit
+    double votes[5] = {(double)M, can_legacy ? 1.0 : 0.0, can_fused ? 1.0 : 0.0, wants_fused ? 1.0 : 0.0,
+                       wants_inplace ? 1.0 : 0.0};
+    if (h->nranks > 1) {
+        DevBuf bVote;
+        CK(bVote.alloc(8 * 8, st));
+        for (int i = 0; i < 5; ++i) h->h_pin[i] = votes[i];
+        CK(cudaMemcpyAsync(bVote.p, h->h_pin, 5 * 8, cudaMemcpyHostToDevice, st));
+        CKR(allreduce(h, bVote.as<double>(), 5, kNcclSum));
+        CK(cudaMemcpyAsync(h->h_pin, bVote.p, 5 * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 5; ++i) votes[i] = h->h_pin[i];
     }
-    bool use_w = syrk_ok && !fused && !hk;
+    Mg = votes[0];
+    const bool all_legacy = votes[1] > (double)h->nranks - 0.5;
+    const bool all_fused = votes[2] > (double)h->nranks - 0.5;
+    bool fused;
+    {
+        const char* env_f = getenv("TLSQ_FUSED");
+        if (env_f) fused = all_fused && atoi(env_f) != 0;
+        else fused = all_fused && (votes[3] > 0.5 || !all_legacy);
+    }
+    bool use_w = all_legacy && !fused;         // neither: generic kernels on every rank
     // the one-pass kernel moves Y / T tiles with TMA (16-byte strides): an odd row count gets a padded leading dimension
     const int64_t ldp = fused ? M + (M & 1) : M;
     bool fact = (use_w || fused) && !no_fact;
@@ -314,20 +337,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     bool inplace_y = false;
     if (fused && !o.E && !o.U && !o.S && !o.Vt) {
         const char* env_ip = getenv("TLSQ_INPLACE_Y");      // test hook
-        if (env_ip) inplace_y = atoi(env_ip) != 0;
-        else {
-            size_t free_b = 0, total_b = 0;
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
-                uint64_t reserved = 0, used = 0;
-                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-                if (reserved > used) free_b += (size_t)(reserved - used);
-            }
-            const size_t need = 2 * mn * 8 + (size_t)4 << 30;
-            inplace_y = need > free_b;
-        }
+        inplace_y = env_ip ? atoi(env_ip) != 0 : votes[4] > 0.5;      // (any rank short of memory -> all in place)
     }
     CK(bY0.alloc((size_t)ldp * N * 8, st));
     if (!inplace_y) CK(bY1.alloc((size_t)ldp * N * 8, st));
@@ -381,14 +391,6 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
 
     // ---- setup (:174-185) --------------------------------------------------------------------------------
     CK(cudaMemsetAsync(dscal, 0, 16 * 8, st));
-    if (h->nranks > 1) {
-        hp[0] = Mg;
-        CK(cudaMemcpyAsync(dscal + 2, hp, 8, cudaMemcpyHostToDevice, st));
-        CKR(allreduce(h, dscal + 2, 1, kNcclSum));
-        CK(cudaMemcpyAsync(hp, dscal + 2, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        Mg = hp[0];
-    }
     if (Mg < (double)N) return set_err(TLSQ_ERR_UNSUPPORTED, "internal: rpca_core needs M >= N");
     const double dmin = (double)N;
 
@@ -520,7 +522,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         }
         if (fused && (svp > kFusedMaxRank || svpb[cur] > kFusedMaxRank)) {
             // rank estimate beyond the fused kernel: materialise W_k once and continue on the streaming pipeline
-            if (ldp != M || inplace_y || !syrk_ok)
+            if (ldp != M || inplace_y || !all_legacy)
                 return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: rank estimate %d exceeds the one-pass kernel's %d and the "
                                "streaming pipeline cannot take over (padded / in-place dual variable)", svp, kFusedMaxRank);
             CK(ensure_w());
