@@ -164,6 +164,14 @@ int tlsq_hankel_mc_f64(tlsq_handle* h, const double* x, int64_t Ns, int64_t D, i
 int tlsq_unhankel_mc_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, int64_t lag, int64_t Ns, int64_t D,
                          double* y);
 
+/* ---- host-only planning helpers (no device needed) ----------------------------------------------------------------
+ * tlsq_plan_pipeline: the per-iteration pipeline every rank of a sharded solve derives from the rank-summed votes
+ *   votes_sum = sum over ranks of {can run the two-kernel pipeline, can run the one-pass kernel, wants the one-pass
+ *   kernel for memory, wants Y in place}; env_fused = -1 (unset) / 0 / 1 mirrors TLSQ_FUSED.
+ * tlsq_plan_hankel_shard: rows [r0, r0 + Kl) of the K Hankel rows that `rank` owns in a sharded lowrankfilter.       */
+int tlsq_plan_pipeline(int nranks, const double* votes_sum, int env_fused, int* fused, int* use_w, int* inplace);
+int tlsq_plan_hankel_shard(int64_t K, int nranks, int rank, int64_t* r0, int64_t* Kl);
+
 /* ---- building blocks exposed for tests and profiling (device pointers) ------------------------------------- */
 /* G (n x n, column-major) = X' X for X: M x n column-major, via the FP64 tensor-core (DMMA) SYRK kernel       */
 int tlsq_gram_f64_dev(tlsq_handle* h, const double* X, int64_t M, int64_t n, double* G);

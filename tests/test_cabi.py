@@ -78,3 +78,43 @@ def test_synthetic_generators_are_deterministic():
     a = T.synth.lowrank_sparse_np(50, 8, 2, 0.1, seed=7)
     b = T.synth.lowrank_sparse_np(50, 8, 2, 0.1, seed=7)
     assert np.array_equal(a, b) and a.flags.f_contiguous
+
+
+def _plan(nranks, votes, env=-1):
+    lib = T.load()
+    f, w, ip = ctypes.c_int(-1), ctypes.c_int(-1), ctypes.c_int(-1)
+    v = (ctypes.c_double * 4)(*[float(x) for x in votes])
+    assert lib.tlsq_plan_pipeline(nranks, v, env, ctypes.byref(f), ctypes.byref(w), ctypes.byref(ip)) == 0
+    return f.value, w.value, ip.value
+
+
+def test_pipeline_choice_is_a_function_of_the_rank_summed_votes():
+    """Sharded solves: the per-iteration pipelines issue different collectives, so the choice must only depend on the
+    votes summed over the ranks (a shard with an odd row count cannot run the two-kernel pipeline: it must pull every
+    rank onto the one-pass kernel, not pick it alone)."""
+    # votes_sum = {can two-kernel, can one-pass, wants one-pass (memory), wants Y in place}
+    assert _plan(8, [8, 8, 0, 0]) == (0, 1, 0)            # everything fits everywhere: two-kernel pipeline
+    assert _plan(8, [7, 8, 0, 0]) == (1, 0, 0)            # one shard cannot run it -> one-pass kernel on ALL ranks
+    assert _plan(8, [8, 8, 1, 0]) == (1, 0, 0)            # one rank short of memory -> one-pass kernel on all
+    assert _plan(8, [8, 8, 1, 1]) == (1, 0, 1)            # ... and Y in place on all
+    assert _plan(8, [7, 7, 0, 0]) == (0, 0, 0)            # neither available everywhere -> generic kernels on all
+    assert _plan(8, [8, 3, 8, 8]) == (0, 1, 1)            # one-pass not available everywhere: stay on two-kernel
+    assert _plan(1, [1, 1, 0, 0], env=1) == (1, 0, 0) and _plan(1, [1, 1, 1, 0], env=0) == (0, 1, 0)
+    assert _plan(2, [2, 1, 0, 0], env=1) == (0, 1, 0)     # forcing cannot override eligibility
+
+
+@pytest.mark.parametrize("K,P", [(49_999_745, 8), (49_999_745, 2), (24_576, 2), (12_000, 8), (461, 4), (7, 8), (100, 1)])
+def test_hankel_row_shards_cover_the_rows_once(K, P):
+    lib = T.load()
+    nxt = 0
+    sizes = []
+    for r in range(P):
+        r0, kl = ctypes.c_int64(-1), ctypes.c_int64(-1)
+        assert lib.tlsq_plan_hankel_shard(K, P, r, ctypes.byref(r0), ctypes.byref(kl)) == 0
+        assert r0.value == nxt and kl.value >= 0
+        nxt += kl.value
+        sizes.append(kl.value)
+    assert nxt == K
+    if K >= 64 * P:
+        assert all(s % 32 == 0 for s in sizes[:-1])       # tile-aligned shards, remainder on the last rank
+        assert max(sizes) - min(sizes) < 32 * P + 32

@@ -192,6 +192,32 @@ int use_device(tlsq_handle* h) {
     return TLSQ_OK;
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Host-only planning logic, shared by the solver and by the CPU test-suite (tlsq_plan_* in the C ABI).
+// ----------------------------------------------------------------------------------------------------------
+// votes_sum = sum over the ranks of {can_legacy, can_fused, wants_fused, wants_inplace} (0/1 each).  The per-iteration
+// pipelines issue different collectives, so every rank must derive the SAME choice from the summed votes.
+struct PipelineChoice { bool fused, use_w, all_legacy, all_fused, inplace_vote; };
+PipelineChoice choose_pipeline(int nranks, const double* votes_sum, int env_fused /* -1: unset */) {
+    PipelineChoice c;
+    c.all_legacy = votes_sum[0] > (double)nranks - 0.5;
+    c.all_fused = votes_sum[1] > (double)nranks - 0.5;
+    if (env_fused >= 0) c.fused = c.all_fused && env_fused != 0;
+    else c.fused = c.all_fused && (votes_sum[2] > 0.5 || !c.all_legacy);
+    c.use_w = c.all_legacy && !c.fused;            // neither: generic kernels on every rank
+    c.inplace_vote = votes_sum[3] > 0.5;           // any rank short of memory -> all ranks update Y in place
+    return c;
+}
+
+// Row shards of the K Hankel rows of lowrankfilter: multiples of 32 rows (TMA / tile friendly), the last rank takes
+// the remainder; tiny problems fall back to a plain split.
+void shard_hankel_rows(int64_t K, int nranks, int rank, int64_t* r0, int64_t* Kl) {
+    int64_t per = ((K + nranks - 1) / nranks + 31) / 32 * 32;
+    if (per * (nranks - 1) >= K) per = K / nranks;
+    *r0 = per * rank;
+    *Kl = (rank == nranks - 1) ? K - *r0 : per;
+}
+
 struct RpcaParams {
     double lambda, tol, rho;
     int64_t maxrank, iters;
@@ -277,15 +303,11 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         for (int i = 0; i < 5; ++i) votes[i] = h->h_pin[i];
     }
     Mg = votes[0];
-    const bool all_legacy = votes[1] > (double)h->nranks - 0.5;
-    const bool all_fused = votes[2] > (double)h->nranks - 0.5;
-    bool fused;
-    {
-        const char* env_f = getenv("TLSQ_FUSED");
-        if (env_f) fused = all_fused && atoi(env_f) != 0;
-        else fused = all_fused && (votes[3] > 0.5 || !all_legacy);
-    }
-    bool use_w = all_legacy && !fused;         // neither: generic kernels on every rank
+    const char* env_f = getenv("TLSQ_FUSED");
+    const PipelineChoice pc = choose_pipeline(h->nranks, votes + 1, env_f ? (atoi(env_f) != 0 ? 1 : 0) : -1);
+    const bool all_legacy = pc.all_legacy;
+    bool fused = pc.fused;
+    bool use_w = pc.use_w;
     // the one-pass kernel moves Y / T tiles with TMA (16-byte strides): an odd row count gets a padded leading dimension
     const int64_t ldp = fused ? M + (M & 1) : M;
     bool fact = (use_w || fused) && !no_fact;
@@ -337,7 +359,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     bool inplace_y = false;
     if (fused && !o.E && !o.U && !o.S && !o.Vt) {
         const char* env_ip = getenv("TLSQ_INPLACE_Y");      // test hook
-        inplace_y = env_ip ? atoi(env_ip) != 0 : votes[4] > 0.5;      // (any rank short of memory -> all in place)
+        inplace_y = env_ip ? atoi(env_ip) != 0 : pc.inplace_vote;     // (any rank short of memory -> all in place)
     }
     CK(bY0.alloc((size_t)ldp * N * 8, st));
     if (!inplace_y) CK(bY1.alloc((size_t)ldp * N * 8, st));
@@ -957,17 +979,16 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
     // sums are taken straight from A_k = clamp(T_k V_k'); sharded runs all-reduce the Ns partial sums.
     {
         static const bool no_fact = getenv("TLSQ_NO_FACTORED") != nullptr;
-        // shard boundaries on multiples of 32 rows (TMA / tile friendly); the last rank takes the remainder
-        int64_t per = ((K + h->nranks - 1) / h->nranks + 31) / 32 * 32;
-        if (per * (h->nranks - 1) >= K) per = K / h->nranks;          // tiny problems: plain split
-        const int64_t r0 = per * h->rank;
-        const int64_t Kl = (h->rank == h->nranks - 1) ? K - r0 : per;
+        int64_t r0, Kl, per, Klast, r0last;
+        shard_hankel_rows(K, h->nranks, h->rank, &r0, &Kl);
+        shard_hankel_rows(K, h->nranks, 0, &r0last, &per);
+        shard_hankel_rows(K, h->nranks, h->nranks - 1, &r0last, &Klast);
         // the decision must be the same on every rank (collectives): test the regular shard and the last one
         auto shard_ok = [&](int64_t rows) {
             return rows >= 1 && (syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), rows, n, rows) ||
                                  fused_eligible(MatSrc{y, 1}, true, rows, n));
         };
-        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && shard_ok(per) && shard_ok(K - per * (h->nranks - 1))) {
+        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && shard_ok(per) && shard_ok(Klast)) {
             CKR(check_rpca_args(Kl, n, p));
             DevBuf bSum;
             CK(bSum.alloc((size_t)Ns * 8, st));
@@ -1442,6 +1463,20 @@ int tlsq_unhankel_mc_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, 
     CK(launch_unhankel_mc(bA.as<double>(), K, L, lag, Ns, D, by.as<double>(), st, &h->launches));
     CK(cudaMemcpyAsync(y, by.as<double>(), (size_t)Ns * D * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return TLSQ_OK;
+}
+
+// ---- host-only planning helpers (no device needed; exercised by the CPU test-suite) -------------------------------
+int tlsq_plan_pipeline(int nranks, const double* votes_sum, int env_fused, int* fused, int* use_w, int* inplace) {
+    if (nranks < 1 || !votes_sum || !fused || !use_w || !inplace) return set_err(TLSQ_ERR_ARG, "plan_pipeline: bad arguments");
+    const PipelineChoice c = choose_pipeline(nranks, votes_sum, env_fused);
+    *fused = c.fused ? 1 : 0; *use_w = c.use_w ? 1 : 0; *inplace = c.inplace_vote ? 1 : 0;
+    return TLSQ_OK;
+}
+
+int tlsq_plan_hankel_shard(int64_t K, int nranks, int rank, int64_t* r0, int64_t* Kl) {
+    if (K < 1 || nranks < 1 || rank < 0 || rank >= nranks || !r0 || !Kl) return set_err(TLSQ_ERR_ARG, "plan_hankel_shard: bad arguments");
+    shard_hankel_rows(K, nranks, rank, r0, Kl);
     return TLSQ_OK;
 }
 
