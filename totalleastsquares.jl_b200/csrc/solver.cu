@@ -988,7 +988,7 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
             return rows >= 1 && (syrk_tma_eligible(reinterpret_cast<const double*>(uintptr_t(256)), rows, n, rows) ||
                                  fused_eligible(MatSrc{y, 1}, true, rows, n));
         };
-        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && shard_ok(per) && shard_ok(Klast)) {
+        if (lag == 1 && !no_fact && K >= n && n <= kEigMaxN && (h->nranks == 1 || shard_ok(per)) && shard_ok(Klast)) {
             CKR(check_rpca_args(Kl, n, p));
             DevBuf bSum;
             CK(bSum.alloc((size_t)Ns * 8, st));
