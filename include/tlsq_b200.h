@@ -171,6 +171,9 @@ int tlsq_unhankel_mc_f64(tlsq_handle* h, const double* A, int64_t K, int64_t L, 
  * tlsq_plan_hankel_shard: rows [r0, r0 + Kl) of the K Hankel rows that `rank` owns in a sharded lowrankfilter.       */
 int tlsq_plan_pipeline(int nranks, const double* votes_sum, int env_fused, int* fused, int* use_w, int* inplace);
 int tlsq_plan_hankel_shard(int64_t K, int nranks, int rank, int64_t* r0, int64_t* Kl);
+/* work split of the one-pass kernel's 256 x 256 Gram: tile_row / strip_col [2 CTAs][8 warps][9 strips] -- strip s of
+ * warp w of CTA r is rows [32 tile_row, +32) x columns [8 strip_col, +8) of the upper triangle                      */
+int tlsq_plan_fused_strips(uint8_t* tile_row, uint8_t* strip_col);
 
 /* ---- building blocks exposed for tests and profiling (device pointers) ------------------------------------- */
 /* G (n x n, column-major) = X' X for X: M x n column-major, via the FP64 tensor-core (DMMA) SYRK kernel       */

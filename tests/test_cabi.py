@@ -118,3 +118,65 @@ def test_hankel_row_shards_cover_the_rows_once(K, P):
     if K >= 64 * P:
         assert all(s % 32 == 0 for s in sizes[:-1])       # tile-aligned shards, remainder on the last rank
         assert max(sizes) - min(sizes) < 32 * P + 32
+
+
+def test_one_pass_kernel_strip_table_covers_the_upper_triangle_once():
+    """fused.cu: the 36 upper 32 x 32 tiles of the 256 x 256 Gram = 144 strips of 32 x 8, 72 per CTA of the cluster pair,
+    9 per warp, every strip exactly once, at most two tile rows per warp (two A-fragment sets), and CTA 0 only touches
+    columns < 192 (it receives columns 128..191 from its peer, nothing else)."""
+    rows = np.zeros((2, 8, 9), dtype=np.uint8)
+    cols = np.zeros((2, 8, 9), dtype=np.uint8)
+    assert T.load().tlsq_plan_fused_strips(rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p)) == 0
+    seen = set()
+    for r in range(2):
+        for w in range(8):
+            assert len(set(rows[r, w].tolist())) <= 2
+            assert sorted(rows[r, w].tolist()) == rows[r, w].tolist()          # first n1 strips share tile row A
+            for s in range(9):
+                a, c = int(rows[r, w, s]), int(cols[r, w, s])
+                assert c // 4 >= a                                              # upper triangle (tile column >= tile row)
+                assert (a, c) not in seen
+                seen.add((a, c))
+                if r == 0:
+                    assert a <= 3 and c < 24
+    assert len(seen) == 144 and seen == {(a, c) for a in range(8) for c in range(4 * a, 32)}
+
+
+def test_hierarchical_jacobi_tournament_visits_every_pair_once_per_sweep():
+    """eig.cu jacobi_cluster_block_kernel, modelled on the host: C CTAs x two half-blocks of spc columns; per outer round
+    the spc x spc cross pairs of a CTA (inner round r: T[w] with B[(w + r) % spc]), in outer round 0 also the pairs
+    inside the half-blocks (circle method), then the half-blocks move (top[0] fixed, top[c] -> top[c+1],
+    top[C-1] -> bot[C-1], bot[c] -> bot[c-1], bot[0] -> top[1])."""
+    for C, spc in [(16, 8), (8, 8), (4, 5), (2, 3), (1, 8), (1, 1)]:
+        ncol = 2 * C * spc
+        top = [list(range(c * 2 * spc, c * 2 * spc + spc)) for c in range(C)]
+        bot = [list(range(c * 2 * spc + spc, (c + 1) * 2 * spc)) for c in range(C)]
+        pairs = []
+        spe = spc + (spc & 1)
+        for orow in range(2 * C - 1):
+            for c in range(C):
+                if orow == 0 and spc > 1:
+                    for half in (top[c], bot[c]):
+                        for r in range(spe - 1):
+                            for pi in range(spe // 2):
+                                p, q = (spe - 1, r) if pi == 0 else ((r + pi) % (spe - 1), (r - pi + spe - 1) % (spe - 1))
+                                if p < spc and q < spc:
+                                    pairs.append(frozenset((half[p], half[q])))
+                for r in range(spc):
+                    for w in range(spc):
+                        pairs.append(frozenset((top[c][w], bot[c][(w + r) % spc])))
+            if C > 1:
+                ntop, nbot = [None] * C, [None] * C
+                for c in range(C):
+                    if c == 0:
+                        ntop[0] = top[0]
+                    elif c == C - 1:
+                        nbot[C - 1] = top[c]
+                    else:
+                        ntop[c + 1] = top[c]
+                    if c == 0:
+                        ntop[1] = bot[0]
+                    else:
+                        nbot[c - 1] = bot[c]
+                top, bot = ntop, nbot
+        assert len(pairs) == len(set(pairs)) == ncol * (ncol - 1) // 2, (C, spc)

@@ -55,6 +55,7 @@ SIGNATURES = {
     "tlsq_unhankel_mc_f64": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]),
     "tlsq_plan_pipeline": (C.c_int, [C.c_int, c_dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int)]),
+    "tlsq_plan_fused_strips": (C.c_int, [vp, vp]),
     "tlsq_plan_hankel_shard": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_i64p, c_i64p]),
     "tlsq_gram_f64_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),
     "tlsq_eigh_f64_dev": (C.c_int, [vp, vp, C.c_int64, vp, vp]),

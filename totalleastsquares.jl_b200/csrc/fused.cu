@@ -920,6 +920,8 @@ cudaError_t launch_rp(bool hankel, const CUtensorMap* m, const FusedDev& p, int 
 
 }  // namespace
 
+FusedStripTab fused_strip_table() { return make_tab(); }
+
 size_t fused_partial_doubles(int sm_count) {
     return (size_t)(sm_count / 2) * FN * FN + (size_t)sm_count + 8 + (size_t)FN * VT_LD;
 }

@@ -200,6 +200,7 @@ struct FusedArgs {
     const double* VpT;      // packed V_{k-1}' scratch inside partial (set by the launcher)
 };
 size_t fused_partial_doubles(int sm_count);
+FusedStripTab fused_strip_table();      // which 32 x 8 Gram strips every (CTA of the pair, warp) accumulates
 bool fused_eligible(const MatSrc& D, bool hankel, int64_t M, int64_t N);
 int fused_rank_pad(int svp, int svp_prev);
 // G (256 x 256) = Gram of the chosen operand; zz_out (nullable) = ||Z_k||_F^2

@@ -1474,6 +1474,14 @@ int tlsq_plan_pipeline(int nranks, const double* votes_sum, int env_fused, int* 
     return TLSQ_OK;
 }
 
+int tlsq_plan_fused_strips(uint8_t* tile_row, uint8_t* strip_col) {
+    if (!tile_row || !strip_col) return set_err(TLSQ_ERR_ARG, "plan_fused_strips: bad arguments");
+    const FusedStripTab t = fused_strip_table();
+    memcpy(tile_row, t.row, sizeof(t.row));
+    memcpy(strip_col, t.cs, sizeof(t.cs));
+    return TLSQ_OK;
+}
+
 int tlsq_plan_hankel_shard(int64_t K, int nranks, int rank, int64_t* r0, int64_t* Kl) {
     if (K < 1 || nranks < 1 || rank < 0 || rank >= nranks || !r0 || !Kl) return set_err(TLSQ_ERR_ARG, "plan_hankel_shard: bad arguments");
     shard_hankel_rows(K, nranks, rank, r0, Kl);
