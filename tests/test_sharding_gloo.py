@@ -77,6 +77,33 @@ def _worker(rank, world, port, q):
         norms = np.sqrt((X * X).sum(axis=0))
         qo, _ = O.rpca_ga_1(norms, X / norms, np.zeros(16), q0[:, 0], iters=1, exact_order=False)
         assert np.allclose(qn, qo[a0:a1], rtol=0, atol=1e-13)
+        # --- pipeline vote of a sharded solve: ranks with DIFFERENT local capabilities must end up with the same
+        #     choice (solver.cu sums {M, can two-kernel, can one-pass, wants one-pass, wants in-place Y} with NCCL) -----
+        import ctypes
+        lib = T.load()
+        for local, expect in [
+            # rank 0 owns an even shard (both pipelines), rank 1 an odd one (one-pass kernel only)
+            (([1, 1, 0, 0], [0, 1, 0, 0]), (1, 0, 0)),
+            # both can do both, rank 1 is short of memory -> one-pass kernel and in-place Y on BOTH ranks
+            (([1, 1, 0, 0], [1, 1, 1, 1]), (1, 0, 1)),
+            # rank 1 cannot run the one-pass kernel (n != 256 shard too short ...) -> two-kernel pipeline on both
+            (([1, 1, 1, 0], [1, 0, 0, 0]), (0, 1, 0)),
+        ]:
+            v = torch.tensor(local[rank], dtype=torch.float64)
+            dist.all_reduce(v)
+            f, w, ip = ctypes.c_int(-1), ctypes.c_int(-1), ctypes.c_int(-1)
+            vv = (ctypes.c_double * 4)(*v.tolist())
+            assert lib.tlsq_plan_pipeline(world, vv, -1, ctypes.byref(f), ctypes.byref(w), ctypes.byref(ip)) == 0
+            assert (f.value, w.value, ip.value) == expect, (rank, local, (f.value, w.value, ip.value))
+        # Hankel row shards of the two ranks tile [0, K) and agree on the "last shard" every rank tests
+        K = 49_999_745
+        r0, kl = ctypes.c_int64(), ctypes.c_int64()
+        assert lib.tlsq_plan_hankel_shard(K, world, rank, ctypes.byref(r0), ctypes.byref(kl)) == 0
+        span = torch.tensor([float(r0.value), float(kl.value)], dtype=torch.float64)
+        both = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(both, span)
+        assert both[0][0].item() == 0 and both[0][1].item() == both[1][0].item()
+        assert both[1][0].item() + both[1][1].item() == K and both[0][1].item() % 32 == 0
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
