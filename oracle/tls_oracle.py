@@ -16,7 +16,8 @@ Pinning status
 * Pinned against every reference-authored fixture for the path (tests/test_oracle.py):
   the 5x5 known-answer test (test/runtests.jl:143-165, atol 1e-6), the exact hankel/unhankel vectors
   (test/runtests.jl:293-294, 361-376), the mu! weighted-mean identity (:469-480), the Q'Q=I invariant
-  (:447-464) and the statistical bounds (:172-185, :378-380, README.md:85-106).
+  (:447-464), the statistical bounds (:172-185, :378-380, README.md:85-106), the soft_hankel! properties
+  (:293-307) and the robust-average identities (:469-488).
 * Beyond those fixtures numerical parity at the LAPACK boundary is **unpinned by the reference's own
   tests**; the oracle run is the pin ("parity unpinned" beyond the 5x5 golden).
 

@@ -48,6 +48,41 @@ def main():
     out["lrf_yf_lag2"] = O.lowrankfilter(yn, 10, lag=2)
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "oracle_vectors.npz"), {k: np.shape(v) for k, v in out.items()})
+    main_ext()
+
+
+def main_ext():
+    """Second fixture file: the branches added after the first one (hankel=true, channels, plain SSA, robust averages)."""
+    out = {}
+    rng = np.random.default_rng(2024)
+    # rpca(...; hankel=true, nukeA=false)  (src/robustPCA.jl:214-216, 234-236)
+    H = O.hankel(rng.standard_normal(300), 12)
+    r = O.rpca(H, hankel=True, nukeA=False, iters=12, tol=0.0)
+    out["hk_H"], out["hk_A"], out["hk_E"], out["hk_hist"] = H, r.A, r.E, r.hist
+    # channels: hankel / unhankel / lowrankfilter on an N x 2 signal  (:53-68, :83-90, :119-128)
+    t = np.arange(1, 301)
+    Y = np.column_stack([np.sin(0.1 * t), np.sin(0.3 * t) + 0.5 * np.sin(0.1 * t)])
+    Yn = Y + 0.1 * rng.standard_normal(Y.shape) + (rng.random(Y.shape) < 0.02) * 5.0
+    out["mc_Yn"] = Yn
+    out["mc_H"] = O.hankel(Yn, 5, 2)
+    out["mc_unh"] = O.unhankel(out["mc_H"], 2, 300, 2)
+    out["mc_yf"] = O.lowrankfilter(Yn, 12)
+    out["mc_yf_ssa"] = O.lowrankfilter(Yn, 12, lag=2, sv=4)
+    # plain SSA on one channel  (:123-125)
+    yn = np.sin(0.1 * t) + rng.standard_normal(300)
+    out["ssa_y"], out["ssa_yf"] = yn, O.lowrankfilter(yn, 20, sv=2)
+    # robust averages of rpca_ga  (:323-333, :349-357)
+    U0, S0, Vt0 = np.linalg.svd(rng.standard_normal((8, 120)), full_matrices=False)
+    X = (U0[:, :2] * S0[:2]) @ Vt0[:2] + 1e-3 * rng.standard_normal((8, 120))
+    X += 1000.0 * rng.standard_normal((8, 120)) * (rng.random((8, 120)) < 0.01)
+    q0 = rng.standard_normal((8, 2))
+    out["ra_X"], out["ra_q0"] = np.asfortranarray(X), np.asfortranarray(q0)
+    Q, its = O.rpca_ga(X, 2, q0=q0, mu=O.entrywise_trimmed_mean, exact_order=False, iters=25, return_iters=True)
+    out["ra_Q_trimmed"], out["ra_its_trimmed"] = Q, np.array(its)
+    Q, its = O.rpca_ga(X, 2, q0=q0, mu=O.entrywise_median, exact_order=False, iters=25, return_iters=True)
+    out["ra_Q_median"], out["ra_its_median"] = Q, np.array(its)
+    np.savez_compressed(os.path.join(HERE, "oracle_vectors_ext.npz"), **out)
+    print("wrote", os.path.join(HERE, "oracle_vectors_ext.npz"), {k: np.shape(v) for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -384,3 +384,19 @@ def test_large_problem_properties():
     # idempotence: the recovered low-rank part is a fixed point (no sparse part left)
     A2, E2, _, sv2 = T.rpca(A, nonnegA=True, want_svd=False)
     assert sv2 == 10 and (torch.linalg.norm(E2) / torch.linalg.norm(A)).item() < 1e-6
+
+
+def test_golden_vectors_extended():
+    """tests/golden/oracle_vectors_ext.npz: hankel=true, channels, plain SSA (continuous maps -> 1e-9 against the
+    committed oracle outputs; the discontinuous robust averages are compared with a live oracle run elsewhere)."""
+    g = np.load(os.path.join(HERE, "golden", "oracle_vectors_ext.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        A, E, s, sv, info = T.rpca(g["hk_H"], hankel=True, nukeA=False, iters=12, tol=0.0, return_info=True)
+    assert relF(A, g["hk_A"]) < TOL and relF(E, g["hk_E"]) < TOL
+    assert np.array_equal(info["hist"][:, 1], g["hk_hist"][:, 1])
+    assert np.array_equal(T.hankel(g["mc_Yn"], 5, 2), g["mc_H"])
+    assert np.allclose(T.unhankel(g["mc_H"], 2, 300, 2), g["mc_unh"], rtol=0, atol=1e-13)
+    assert relF(T.lowrankfilter(g["mc_Yn"], 12), g["mc_yf"]) < TOL
+    assert relF(T.lowrankfilter(g["mc_Yn"], 12, lag=2, sv=4), g["mc_yf_ssa"]) < TOL
+    assert relF(T.lowrankfilter(g["ssa_y"], 20, sv=2), g["ssa_yf"]) < TOL

@@ -179,3 +179,39 @@ def test_robust_averages_match_the_reference_identities():
     q0 = rng.standard_normal((6, 2))
     Q = O.rpca_ga(X, 2, q0=q0, mu=O.entrywise_trimmed_mean, exact_order=False, iters=50)
     assert np.all(np.isfinite(Q)) and np.allclose(np.linalg.norm(Q, axis=0), 1.0)
+
+
+def test_oracle_reproduces_the_extended_golden_file():
+    """tests/golden/oracle_vectors_ext.npz (hankel=true, channels, plain SSA, robust averages) is what the CUDA path is
+    compared with on the GPU box; the oracle must keep reproducing it."""
+    import warnings
+    g = np.load(os.path.join(HERE, "golden", "oracle_vectors_ext.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = O.rpca(g["hk_H"], hankel=True, nukeA=False, iters=12, tol=0.0)
+    assert np.allclose(r.A, g["hk_A"], rtol=0, atol=1e-12) and np.allclose(r.E, g["hk_E"], rtol=0, atol=1e-12)
+    assert O.ishankel(O.rpca(g["hk_H"], hankel=True, nukeA=False).A)          # test/runtests.jl:331
+    assert np.array_equal(O.hankel(g["mc_Yn"], 5, 2), g["mc_H"])
+    assert np.allclose(O.unhankel(g["mc_H"], 2, 300, 2), g["mc_unh"], rtol=0, atol=1e-14)
+    assert np.allclose(O.lowrankfilter(g["mc_Yn"], 12), g["mc_yf"], rtol=0, atol=1e-10)
+    assert np.allclose(O.lowrankfilter(g["mc_Yn"], 12, lag=2, sv=4), g["mc_yf_ssa"], rtol=0, atol=1e-10)
+    assert np.allclose(O.lowrankfilter(g["ssa_y"], 20, sv=2), g["ssa_yf"], rtol=0, atol=1e-10)
+    for name, mu in (("trimmed", O.entrywise_trimmed_mean), ("median", O.entrywise_median)):
+        Q, its = O.rpca_ga(g["ra_X"], 2, q0=g["ra_q0"], mu=mu, exact_order=False, iters=25, return_iters=True)
+        assert list(its) == list(g[f"ra_its_{name}"]) and np.allclose(Q, g[f"ra_Q_{name}"], rtol=0, atol=1e-10)
+
+
+def test_soft_hankel_reference_properties():
+    """test/runtests.jl:296-307: soft_hankel! pulls a noisy Hankel matrix towards the clean one (both signs)."""
+    rng = np.random.default_rng(5)
+    A = O.hankel(np.arange(1.0, 9.0), 4)
+    assert O.ishankel(A)
+    for sgn in (1.0, -1.0):
+        An = sgn * A + 0.1 * rng.standard_normal(A.shape)
+        assert not O.ishankel(An)
+        Anc = An.copy()
+        O.soft_hankel(An, 0.1)
+        assert np.sum((An - sgn * A) ** 2) < np.sum((Anc - sgn * A) ** 2)
+    assert np.array_equal(O.hankel(np.arange(1, 21), 2), np.column_stack([np.arange(1, 20), np.arange(2, 21)]))
+    assert np.array_equal(O.hankel(np.arange(1, 21), 3, 2),
+                          np.column_stack([np.arange(1, 18, 2), np.arange(2, 19, 2), np.arange(3, 20, 2)]))
