@@ -435,7 +435,7 @@ __global__ void jacobi_global_init_kernel(const double* __restrict__ X0, const d
 __global__ void __launch_bounds__(256)
 eig_post_kernel(const double* __restrict__ Xo, const double* __restrict__ Vo, int n, int ncols,
                 double* __restrict__ lam_raw, double* __restrict__ lam_sorted, int* __restrict__ perm,
-                const int* __restrict__ run_flag) {
+                const int* __restrict__ run_flag, int svd_mode) {
     if (run_flag && run_flag[1] == 0) return;
     extern __shared__ double sl[];          // ncols lam + ncols valid flags (as double)
     double* lam = sl;
@@ -445,11 +445,13 @@ eig_post_kernel(const double* __restrict__ Xo, const double* __restrict__ Vo, in
         double dot = 0.0, vv = 0.0;
         for (int i = lane; i < n; i += 32) {
             const double v = Vo[(int64_t)j * n + i];
-            dot = fma(v, Xo[(int64_t)j * n + i], dot);
+            const double x = Xo[(int64_t)j * n + i];
+            dot = fma(svd_mode ? x : v, x, dot);                   // svd mode: |x_j|^2 (X = K V, K general square)
             vv = fma(v, v, vv);
         }
         dot = warp_sum(dot);
         vv = warp_sum(vv);
+        if (svd_mode) dot = sqrt(dot);                             // singular value of K
         if (lane == 0) {
             lam[j] = dot;
             valid[j] = (vv > 0.5) ? 1.0 : 0.0;
@@ -504,6 +506,69 @@ __global__ void svt_post_kernel(const double* __restrict__ lam, int n, double ta
     if (threadIdx.x == 0) *svp = cnt;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Upper Cholesky factor R (R'R = A) of a small SPD matrix, single CTA, right-looking, the matrix stays in global
+// memory (L2 resident).  Used once per solve by the SVD refinement (solver.cu): A = C'C with C = W V diag(1/s) nearly
+// orthonormal, so A is close to the identity.  A pivot that has lost all its digits (<= n eps times its original
+// value: the column depends on the previous ones, e.g. an exactly rank-deficient W) deflates: its row of R is zero.
+// R: n x n column-major, strictly lower part zeroed.  In place: R must hold A on entry.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+chol_upper_kernel(double* __restrict__ R, int n) {
+    extern __shared__ double rowj[];            // [n] scaled row j, then [n] original diagonal
+    double* d0 = rowj + n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int i = tid; i < n; i += blockDim.x) d0[i] = R[(int64_t)i * n + i];
+    __syncthreads();
+    const double epsn = 2.220446049250313e-16 * (double)n;
+    for (int j = 0; j < n; ++j) {
+        __syncthreads();                         // the trailing update of step j-1 is complete
+        const double ajj = R[(int64_t)j * n + j];
+        const bool ok = ajj > epsn * d0[j] && d0[j] > 0.0;
+        const double piv = ok ? sqrt(ajj) : 0.0;
+        const double ipiv = ok ? 1.0 / piv : 0.0;
+        __syncthreads();                         // everybody has read the pivot before it is overwritten
+        for (int k = j + tid; k < n; k += blockDim.x) {
+            const double v = (k == j) ? piv : R[(int64_t)k * n + j] * ipiv;
+            rowj[k] = v;
+            R[(int64_t)k * n + j] = v;
+        }
+        __syncthreads();
+        if (ok) {
+            for (int k = j + 1 + warp; k < n; k += nw) {
+                const double rjk = rowj[k];
+                double* col = R + (int64_t)k * n;
+                for (int i = j + 1 + lane; i <= k; i += 32) col[i] = fma(-rowj[i], rjk, col[i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int64_t idx = tid; idx < (int64_t)n * n; idx += blockDim.x) {
+        const int i = (int)(idx % n), k = (int)(idx / n);
+        if (i > k) R[idx] = 0.0;
+    }
+}
+
+// B[:, c] = V[:, c] / max(s_c, floor * s_0)   (st_out[c] = the clamped scale)
+__global__ void scale_cols_floor_kernel(const double* __restrict__ V, const double* __restrict__ sigma, int n,
+                                        double floor_rel, double* __restrict__ B, double* __restrict__ st_out) {
+    const int c = blockIdx.x;
+    double s = sigma[c];
+    const double fl = floor_rel * sigma[0];
+    if (!(s > fl)) s = fl;
+    const double f = s > 0.0 ? 1.0 / s : 0.0;
+    if (threadIdx.x == 0) st_out[c] = s;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) B[(int64_t)c * n + i] = V[(int64_t)c * n + i] * f;
+}
+// K[:, c] = R[:, c] * st[c]
+__global__ void scale_cols_mul_kernel(const double* __restrict__ R, const double* __restrict__ st, int n,
+                                      double* __restrict__ K) {
+    const int c = blockIdx.x;
+    const double s = st[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) K[(int64_t)c * n + i] = R[(int64_t)c * n + i] * s;
+}
+
 template <int E>
 cudaError_t launch_cluster(const double* X0, const double* V0, int n, int C, int spc, double tol, int max_sweeps,
                            double* Xo, double* Vo, int* info, const int* run_flag, cudaStream_t st) {
@@ -552,7 +617,7 @@ size_t eig_work_doubles(int n) {
 }
 
 cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
-                        int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag) {
+                        int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag, int svd_mode) {
     cudaError_t e;
     const double tol = 1.0e-15 * (n < 16 ? 4.0 : sqrt((double)n));   // relative orthogonality threshold
     const int max_sweeps = 30;
@@ -588,10 +653,38 @@ cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, dou
         if (e != cudaSuccess) return e;
         if (launches) *launches += 2;
     }
-    eig_post_kernel<<<1, 256, 2 * ncols * sizeof(double), st>>>(w.Xo, w.Vo, n, ncols, w.lam_raw, lam, w.perm, run_flag);
+    eig_post_kernel<<<1, 256, 2 * ncols * sizeof(double), st>>>(w.Xo, w.Vo, n, ncols, w.lam_raw, lam, w.perm, run_flag,
+                                                                 svd_mode);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     permute_cols_kernel<<<n, 128, 0, st>>>(w.Vo, w.perm, n, Vs, run_flag);
     if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chol_upper(double* R, int n, cudaStream_t st, int64_t* launches) {
+    chol_upper_kernel<<<1, 1024, 2 * (size_t)n * sizeof(double), st>>>(R, n);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_cols_floor(const double* V, const double* sigma, int n, double floor_rel, double* B,
+                                    double* st_out, cudaStream_t st, int64_t* launches) {
+    scale_cols_floor_kernel<<<n, 128, 0, st>>>(V, sigma, n, floor_rel, B, st_out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_cols_mul(const double* R, const double* sc, int n, double* K, cudaStream_t st,
+                                  int64_t* launches) {
+    scale_cols_mul_kernel<<<n, 128, 0, st>>>(R, sc, n, K);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_nn(const double* A, const double* B, int n, double* C, cudaStream_t st, int64_t* launches) {
+    dim3 grid((n + 31) / 32, (n + 31) / 32);
+    gemm_small_kernel<<<grid, 256, 0, st>>>(A, B, n, C);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

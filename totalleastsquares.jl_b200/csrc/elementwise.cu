@@ -62,14 +62,15 @@ init_ya_kernel(const MatSrc D, int64_t M, int64_t N, double dual, double* __rest
 template <bool HANKEL>
 __global__ void __launch_bounds__(256)
 compute_e_kernel(const MatSrc D, int64_t M, int64_t N, const double* __restrict__ A, const double* __restrict__ Y,
-                 double im, double eps, int nonnegE, double* __restrict__ E) {
+                 double im, double eps, int nonnegE, double* __restrict__ E, double* __restrict__ Wout) {
     const int64_t total = M * N;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = idx % M, col = idx / M;
         double e, w;
         alm_ew(src_at<HANKEL>(D, row, col), A[idx], Y[idx], im, eps, nonnegE, e, w);
-        E[idx] = e;
+        if (E) E[idx] = e;
+        if (Wout) Wout[idx] = w;
     }
 }
 
@@ -194,6 +195,25 @@ unhankel_factors_kernel(const double* __restrict__ T, int64_t ldt, const double*
             }
             sum[k] = s;
         }
+    }
+}
+
+// Same result without shared-memory staging (V and T through the read-only path): taken when [n][rp] + [rp][span] does
+// not fit in shared memory (n > 256 with a large rank estimate).  Once per solve, latency is irrelevant.
+__global__ void __launch_bounds__(256)
+unhankel_factors_direct_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ V, int rp,
+                               int nonnegA, int64_t r0, int64_t Kl, int n, int64_t Ns, double* __restrict__ sum) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < Ns; k += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const int64_t i = k - r0 - j;
+            if (i < 0 || i >= Kl) continue;
+            double av = 0.0;
+            for (int c = 0; c < rp; ++c) av = fma(__ldg(T + (int64_t)c * ldt + i), __ldg(V + (int64_t)c * n + j), av);
+            if (nonnegA) av = (__double_as_longlong(av) > 0) ? av : 0.0;
+            s += av;
+        }
+        sum[k] = s;
     }
 }
 
@@ -344,10 +364,10 @@ cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, d
 
 cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N, const double* A, const double* Y,
                              double im, double eps, int nonnegE, double* E, int sm_count, cudaStream_t st,
-                             int64_t* launches) {
+                             int64_t* launches, double* Wout) {
     const int grid = stream_grid(M * N, sm_count);
-    if (hankel) compute_e_kernel<true><<<grid, 256, 0, st>>>(D, M, N, A, Y, im, eps, nonnegE, E);
-    else compute_e_kernel<false><<<grid, 256, 0, st>>>(D, M, N, A, Y, im, eps, nonnegE, E);
+    if (hankel) compute_e_kernel<true><<<grid, 256, 0, st>>>(D, M, N, A, Y, im, eps, nonnegE, E, Wout);
+    else compute_e_kernel<false><<<grid, 256, 0, st>>>(D, M, N, A, Y, im, eps, nonnegE, E, Wout);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -397,7 +417,13 @@ cudaError_t launch_unhankel_factors(const double* T, int64_t ldt, const double* 
     if (svp < 1) return cudaMemsetAsync(sum, 0, (size_t)Ns * sizeof(double), st);     // A = 0
     const int rp = svp;
     const size_t smem = ((size_t)n * rp + (size_t)rp * (256 + n - 1)) * sizeof(double);
-    if (smem > (size_t)220 * 1024) return cudaErrorInvalidValue;
+    if (smem > (size_t)220 * 1024) {
+        int64_t blocks = (Ns + 255) / 256;
+        if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+        unhankel_factors_direct_kernel<<<(unsigned)blocks, 256, 0, st>>>(T, ldt, V, rp, nonnegA, r0, Kl, (int)n, Ns, sum);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(unhankel_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -104,6 +104,41 @@ gemm_xb_kernel(const double* __restrict__ X, int64_t M, int K, int64_t ldx, cons
         }
 }
 
+// any shape / alignment: 32 x 32 output tile, K in 32-wide chunks through shared memory, plain FP64 FMA
+__global__ void __launch_bounds__(256)
+gemm_plain_kernel(const double* __restrict__ X, int64_t M, int K, int64_t ldx, const double* __restrict__ B, int N,
+                  double* __restrict__ C) {
+    __shared__ double Xs[32][33];      // [k][row]
+    __shared__ double Bs[32][33];      // [col][k]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int kk = ty + 8 * q;
+            Xs[kk][tx] = (r0 + tx < M && k0 + kk < K) ? X[(int64_t)(k0 + kk) * ldx + r0 + tx] : 0.0;
+            Bs[kk][tx] = (c0 + kk < N && k0 + tx < K) ? B[(int64_t)(c0 + kk) * K + k0 + tx] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = ty + 8 * q;
+            double a = acc[q];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) a = fma(Xs[kk][tx], Bs[cc][kk], a);
+            acc[q] = a;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int cc = c0 + ty + 8 * q;
+        if (r0 + tx < M && cc < N) C[(int64_t)cc * M + r0 + tx] = acc[q];
+    }
+}
+
 __global__ void scale_cols_inv_kernel(const double* __restrict__ V, const double* __restrict__ sigma, int n,
                                       double* __restrict__ B) {
     const int c = blockIdx.x;
@@ -130,6 +165,16 @@ cudaError_t launch_gemm_xb(const double* X, int64_t M, int K, int64_t ldx, const
     }
     dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT));
     gemm_xb_kernel<<<grid, 256, smem, st>>>(X, M, K, ldx, B, N, C);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_any(const double* X, int64_t M, int K, int64_t ldx, const double* B, int N, double* C,
+                            cudaStream_t st, int64_t* launches) {
+    if (gemm_xb_eligible(X, M, K, ldx, N) && !(reinterpret_cast<uintptr_t>(B) & 15))
+        return launch_gemm_xb(X, M, K, ldx, B, N, C, st, launches);
+    dim3 grid((unsigned)((M + 31) / 32), (unsigned)((N + 31) / 32));
+    gemm_plain_kernel<<<grid, 256, 0, st>>>(X, M, K, ldx, B, N, C);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

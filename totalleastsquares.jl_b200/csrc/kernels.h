@@ -70,8 +70,20 @@ size_t eig_work_doubles(int n);
 // warm-start basis (previous eigenvectors).  Outputs: lam (n, descending), Vs (n x n sorted eigenvector columns).
 // Vs may alias V0.
 // run_flag (optional, device): the whole decomposition is skipped on the device when run_flag[1] == 0.
+// svd_mode != 0: G is a GENERAL square matrix K; its columns are orthogonalised (K V = U S): lam = singular values
+// (descending), Vs = right singular vectors.
 cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
-                        int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag = nullptr);
+                        int sm_count, cudaStream_t st, int64_t* launches, const int* run_flag = nullptr,
+                        int svd_mode = 0);
+// in-place upper Cholesky factor of an n x n SPD matrix (single CTA; deflates pivots that lost all their digits)
+cudaError_t launch_chol_upper(double* R, int n, cudaStream_t st, int64_t* launches);
+// B[:, c] = V[:, c] / max(sigma_c, floor_rel * sigma_0), sc_out[c] = that scale;   K[:, c] = R[:, c] * sc[c]
+cudaError_t launch_scale_cols_floor(const double* V, const double* sigma, int n, double floor_rel, double* B,
+                                    double* sc_out, cudaStream_t st, int64_t* launches);
+cudaError_t launch_scale_cols_mul(const double* R, const double* sc, int n, double* K, cudaStream_t st,
+                                  int64_t* launches);
+// C = A B for n x n column-major matrices
+cudaError_t launch_gemm_nn(const double* A, const double* B, int n, double* C, cudaStream_t st, int64_t* launches);
 
 // Fast path (eig_fast.cu, 64 < n <= 512; 16-column block only above n = 256): warm-started block subspace iteration for the dominant eigenpairs +
 // a rigorous certificate of the count #{sigma >= tau}.  flags[1] != 0 afterwards means "fall back to launch_eigh".
@@ -147,8 +159,12 @@ cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_c
 // Streaming form of the epilogue (stream.cu) for a materialised W and svp <= kStreamMaxRank (svp known on the host):
 // T (M x 32 workspace) = W V_r diag(f), then one coalesced element-wise pass.  Needs a.Wn != nullptr.
 constexpr int kStreamMaxRank = 32;
+// svp_on_device: `svp` is only a GUESS used to pick the rank specialisation; the kernels read the actual rank from the
+// device scalar a.svp and return without touching anything when it exceeds stream_rank_pad(svp, a.svp_prev, fact)
+// (the caller compares after its next host sync and relaunches).
 cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count,
-                                   cudaStream_t st, int64_t* launches);
+                                   cudaStream_t st, int64_t* launches, bool svp_on_device = false);
+int stream_rank_pad(int svp, int svp_prev, bool fact);
 // can the factored form be used for this (N, svp, svp_prev)?  (two N x RP blocks of V must fit in shared memory)
 bool stream_factored_fits(int64_t N, int svp, int svp_prev);
 // dense helpers for the factored iterate:  A = clamp(T V')   and   Z = (D - A_k) - E_k  with A_{k-1}, A_k factored
@@ -160,6 +176,9 @@ cudaError_t launch_final_from_factors(const EpiArgs& a, bool hankel, int svp, do
 // the left singular vectors U = W V diag(1/s) of the returned SVD (:238)
 cudaError_t launch_gemm_xb(const double* X, int64_t M, int K, int64_t ldx, const double* B, int N, double* C,
                            cudaStream_t st, int64_t* launches);
+// same product for any shape / alignment: the DMMA kernel when eligible, else a plain shared-memory-tiled FP64 kernel
+cudaError_t launch_gemm_any(const double* X, int64_t M, int K, int64_t ldx, const double* B, int N, double* C,
+                            cudaStream_t st, int64_t* launches);
 bool gemm_xb_eligible(const double* X, int64_t M, int K, int64_t ldx, int N);
 // B[:, c] = V[:, c] * (s_c > 0 ? 1/s_c : 0)
 cudaError_t launch_scale_cols_inv(const double* V, const double* sigma, int n, double* B, cudaStream_t st,
@@ -216,9 +235,10 @@ cudaError_t launch_init_ya(const MatSrc& D, bool hankel, int64_t M, int64_t N, d
                            double* W, double im, double eps, int nonnegE, int sm_count, cudaStream_t st,
                            int64_t* launches, int64_t ldy = 0 /* leading dimension of Y; 0 = M */);
 // E = soft_th((D - A) + Y/mu, lambda/mu) (+ clamp)
+// (E and / or the SVT input Wout = (D - E) + Y/mu; null outputs are skipped)
 cudaError_t launch_compute_e(const MatSrc& D, bool hankel, int64_t M, int64_t N, const double* A, const double* Y,
                              double im, double eps, int nonnegE, double* E, int sm_count, cudaStream_t st,
-                             int64_t* launches);
+                             int64_t* launches, double* Wout = nullptr);
 // out (N x M) = in (M x N)'
 cudaError_t launch_transpose(const double* in, int64_t M, int64_t N, double* out, cudaStream_t st,
                              int64_t* launches);

@@ -107,8 +107,9 @@ struct tlsq_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // output pass of the finalisation overlaps the full eigensolver
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_iter = nullptr;
     int64_t launches = 0;
+    cudaMemPool_t pool = nullptr;         // private stream-ordered pool (release threshold: keep everything)
     void* comm = nullptr;
     int nranks = 1;
     int rank = 0;
@@ -125,12 +126,18 @@ struct tlsq_handle {
 
 namespace {
 
+// stream-ordered allocations come from the calling handle's PRIVATE memory pool (set by use_device): freed blocks stay
+// cached between solves without touching the attributes of the device's default pool, which a co-resident allocator
+// (PyTorch) may be using
+thread_local cudaMemPool_t t_pool = nullptr;
+
 struct DevBuf {                  // stream-ordered device allocation, freed on scope exit
     void* p = nullptr;
     cudaStream_t st = nullptr;
     cudaError_t alloc(size_t bytes, cudaStream_t s) {
         st = s;
         if (bytes == 0) bytes = 8;
+        if (t_pool) return cudaMallocFromPoolAsync(&p, bytes, t_pool, s);
         return cudaMallocAsync(&p, bytes, s);
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -189,6 +196,7 @@ int allreduce(tlsq_handle* h, double* buf, size_t count, int op) {
 int use_device(tlsq_handle* h) {
     if (!h) return set_err(TLSQ_ERR_ARG, "null handle");
     CK(cudaSetDevice(h->device));
+    t_pool = h->pool;
     return TLSQ_OK;
 }
 
@@ -230,11 +238,16 @@ struct RpcaOut {
     double* uh_sum = nullptr;  int64_t uh_r0 = 0;  int64_t uh_Ns = 0;
 };
 
+int gram_dense(tlsq_handle* h, const double* X, int64_t M, int64_t n, double* G);
+
 // ----------------------------------------------------------------------------------------------------------
 // rpca core: M (local rows) x N, M_global >= N, N <= kEigMaxN.  D may be dense or an implicit Hankel signal.
 // All outputs are DEVICE pointers (nullable) except sv / iters_done / converged / hist (host).
 // ----------------------------------------------------------------------------------------------------------
-int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const RpcaParams& p, const RpcaOut& o) {
+constexpr int kRetryTwoPhase = -7701;      // internal: rerun with the two-phase iteration forced from *escape_at on
+
+int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const RpcaParams& p, const RpcaOut& o,
+                   int64_t two_phase_from, int64_t* escape_at) {
     cudaStream_t st = h->stream;
     const int sms = h->sm_count;
     int64_t* L = &h->launches;
@@ -274,8 +287,8 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     auto device_free_bytes = [&]() -> size_t {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+        cudaMemPool_t pool = h->pool;
+        if (pool || cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
             uint64_t reserved = 0, used = 0;
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
@@ -286,7 +299,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     const size_t free_b = device_free_bytes();
     const size_t ws_bytes = (size_t)4 << 30;
     bool can_fused = !no_fact && !hk && fused_eligible(D, hankel, M, N);
-    if (can_fused && !syrk_ok && (o.A || o.E || o.U)) can_fused = false;   // padded leading dimension: factored outputs only
+    if (can_fused && !syrk_ok && (o.A || o.E || o.U || o.S || o.Vt)) can_fused = false;   // padded leading dimension: factored outputs only
     const bool can_legacy = syrk_ok && !hk;
     const bool wants_fused = 4 * mn * 8 + mn * 2 + ws_bytes > free_b;      // Y x 2, W, Z (+ factors) do not fit
     const bool wants_inplace = 2 * mn * 8 + mn * 2 + ws_bytes > free_b;    // not even two copies of Y fit
@@ -341,7 +354,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         fa.zpart = fa.partial + (size_t)(sms / 2) * n * n;
     }
 
-    DevBuf bA0, bA1, bY0, bY1, bPart, bG, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
+    DevBuf bA0, bA1, bY0, bY1, bPart, bG, bGn, bG2, bVs, bVs2, bLam, bLam2, bSig, bF, bEig, bScal, bSvp;
     // dense A ping-pong (reusing the caller's A buffer as one side when given); allocated lazily in factored mode
     double* Abuf[2] = {nullptr, nullptr};
     auto alloc_dense_a = [&]() -> cudaError_t {
@@ -365,13 +378,19 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     if (!inplace_y) CK(bY1.alloc((size_t)ldp * N * 8, st));
     double* Ybuf[2] = {bY0.as<double>(), inplace_y ? bY0.as<double>() : bY1.as<double>()};
     CK(bPart.alloc(part_bytes, st));
-    CK(bG.alloc(((size_t)n * n + 8) * 8, st)); CK(bG2.alloc(((size_t)n * n + 8) * 8, st));
+    CK(bG.alloc(((size_t)n * n + 8) * 8, st)); CK(bGn.alloc(((size_t)n * n + 8) * 8, st));
+    CK(bG2.alloc(((size_t)n * n + 8) * 8, st));
     CK(bVs.alloc((size_t)n * n * 8, st)); CK(bVs2.alloc((size_t)n * n * 8, st));
     CK(bLam.alloc((size_t)n * 8, st)); CK(bLam2.alloc((size_t)n * 8, st));
     CK(bSig.alloc((size_t)n * 8, st)); CK(bF.alloc((size_t)n * 8, st));
     CK(bEig.alloc(eig_work_doubles(n) * 8, st));
     CK(bScal.alloc(16 * 8, st)); CK(bSvp.alloc(16, st));
-    double* G = bG.as<double>(); double* G2 = bG2.as<double>();     // [n*n] Gram, [n*n] = ||Z||_F^2 (fused path)
+    // Gram ping-pong: Gb[gi] holds the Gram of the current iteration's SVT input while the next one (one-pass kernel,
+    // run-ahead) is formed in the other buffer -- so the last iteration's Gram survives for the returned SVD (:238).
+    // Slot [n*n] carries ||Z||_F^2 in the packed all-reduce of the one-pass pipeline.
+    double* Gb[2] = {bG.as<double>(), bGn.as<double>()};
+    int gi = 0;
+    double* G2 = bG2.as<double>();
     double* Vs = bVs.as<double>(); double* Vs2 = bVs2.as<double>();
     double* lam = bLam.as<double>(); double* lam2 = bLam2.as<double>();
     double* sigma = bSig.as<double>(); double* fvec = bF.as<double>();
@@ -422,27 +441,27 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     {
         Phase ph(h, TLSQ_PHASE_INIT);
         if (syrk_ok && !hankel && syrk_tma_eligible(D.p, M, N, D.ld)) {
-            CK(launch_syrk_tma(D.p, M, N, D.ld, splan, bPart.as<double>(), G, st, L));   // D'D
+            CK(launch_syrk_tma(D.p, M, N, D.ld, splan, bPart.as<double>(), Gb[0], st, L));   // D'D
         } else if (fused) {
             FusedArgs f0 = fa;
             f0.gram_of = FUSED_GRAM_D;
-            CK(launch_alm_fused(f0, hankel, nullptr, nullptr, nullptr, G, nullptr, sms, st, L));
+            CK(launch_alm_fused(f0, hankel, nullptr, nullptr, nullptr, Gb[0], nullptr, sms, st, L));
         } else {
-            CK(launch_gram(gs, GRAM_D, hankel, plan, bPart.as<double>(), G, st, L));
+            CK(launch_gram(gs, GRAM_D, hankel, plan, bPart.as<double>(), Gb[0], st, L));
         }
-        CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+        CKR(allreduce(h, Gb[0], (size_t)n * n, kNcclSum));
         CK(launch_maxabs(D, hankel, M, N, dscal + 1, sms, st, L));                       // norm(Y, Inf)   :178
         CKR(allreduce(h, dscal + 1, 1, kNcclMax));
         // opnorm(Y) (:177) needs only lambda_max(D'D): dominant-subspace iteration from a cold start with a
         // certificate that theta_1 is the largest eigenvalue; the full Jacobi is the fallback
         if (fast_ok) {
             CK(launch_init_block(fw.Qb, n, st, L));
-            CK(launch_eig_fast(G, n, 0.0, 1, fw, lam, Vs, sigma, fvec, dsvp, st, L, 1, 16));
-            CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
+            CK(launch_eig_fast(Gb[0], n, 0.0, 1, fw, lam, Vs, sigma, fvec, dsvp, st, L, 1, 16));
+            CK(launch_eigh(Gb[0], n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
             CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
             have_q = true;
         } else {
-            CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
+            CK(launch_eigh(Gb[0], n, nullptr, ew, lam, Vs, sms, st, L));
         }
     }
     CK(cudaMemcpyAsync(hp, lam, 8, cudaMemcpyDeviceToHost, st));
@@ -463,8 +482,8 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             // Gram of the first SVT input W_1 = (D - E_1) + Y_0/mu_1 (A_0 = 0), formed on the fly
             FusedArgs f1 = fa;
             f1.gram_of = FUSED_GRAM_W; f1.im = 1.0 / mu; f1.eps = p.lambda / mu;
-            CK(launch_alm_fused(f1, hankel, Ybuf[0], nullptr, nullptr, G, nullptr, sms, st, L));
-            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+            CK(launch_alm_fused(f1, hankel, Ybuf[0], nullptr, nullptr, Gb[0], nullptr, sms, st, L));
+            CKR(allreduce(h, Gb[0], (size_t)n * n, kNcclSum));
             gram_ready = true;
         }
     }
@@ -476,58 +495,78 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     double im_last = 0.0, eps_last = 0.0;
     int prev_idx = 0, last_idx = 0;
     static const bool dbg_eig = getenv("TLSQ_DEBUG_EIG") != nullptr;
+    // Host/device overlap of the two-kernel pipeline (no blocking host sync between the eigen step and the epilogue, and
+    // none between the epilogue and the next Gram):
+    //  * the streaming epilogue is launched on a GUESS of the rank (the previous iteration's) and reads the actual svp
+    //    from device memory; a guess that turns out too small makes the kernels return untouched and is relaunched;
+    //  * while the host waits for ||Z||_F^2 of iteration k, the Gram and the eigen step of iteration k+1 are already
+    //    enqueued ("run-ahead"; skipped when iteration k may converge, so at most nothing is wasted in practice).
+    static const bool no_ahead = getenv("TLSQ_NO_RUNAHEAD") != nullptr;
+    bool ahead_done = false;       // Gram + eigen step of the coming iteration are already enqueued
+    bool eig_stale = false;        // lam / Vs / sigma belong to a run-ahead eigen step, not to the last finished iteration
+    int64_t n_redo = 0;
+
+    // eigen step of one iteration on Gsrc: sigma, V_r, svp = #{sigma >= im}  (:193-204)
+    auto enqueue_eig = [&](const double* Gsrc, double im_k) -> int {
+        Phase ph(h, TLSQ_PHASE_EIG);
+        // a 16-column block is enough while the rank estimate stays <= 10 (it must stay <= block - 2); widening
+        // the block needs an orthonormal 32-column basis, which the next full Jacobi provides
+        const int want_bw = svp_last <= 10 ? 16 : 32;
+        if (want_bw > cur_bw) { have_q = false; cur_bw = 32; }
+        const bool block_fits = cur_bw <= eig_fast_max_block(n);      // n > 256: only the 16-column block
+        if (fast_ok && have_q && block_fits) {
+            // dominant eigenpairs + certified count; the full Jacobi below only runs (device-side flag) when the
+            // fast path could not prove the count
+            CK(launch_eig_fast(Gsrc, n, im_k, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L, 0, cur_bw, si_budget));
+            CK(launch_eigh(Gsrc, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
+            CK(launch_svt_post(lam, n, im_k, nukeA, sigma, fvec, dsvp, st, L, fw.flags));   // :198
+            CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
+            last_was_fast = true;
+        } else {
+            CK(launch_eigh(Gsrc, n, nullptr, ew, lam, Vs, sms, st, L));
+            CK(launch_svt_post(lam, n, im_k, nukeA, sigma, fvec, dsvp, st, L));          // :198
+            if (fast_ok) { CK(launch_copy_block(Vs, n, fw.Qb, nullptr, st, L)); have_q = true; }
+            last_was_fast = false;
+        }
+        return TLSQ_OK;
+    };
 
     for (int64_t k = 1; k <= p.iters; ++k) {                                             // :186
         const int nxt = cur ^ 1;
         const double im = 1.0 / mu;
         const double eps = p.lambda / mu;
+        double* G = Gb[gi];
+        double* Gnext = Gb[gi ^ 1];
         // SVT input Gram  (:188-194)
         gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = nullptr; gs.im = im; gs.eps = eps;
-        if (!gram_ready) {
-            {
-                Phase ph(h, TLSQ_PHASE_GRAM);
-                if (use_w) CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), G, st, L));
-                else CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+        if (!ahead_done) {
+            if (!gram_ready) {
+                {
+                    Phase ph(h, TLSQ_PHASE_GRAM);
+                    if (use_w) CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), G, st, L));
+                    else CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
+                }
+                CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
             }
-            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+            CKR(enqueue_eig(G, im));
         }
         gram_ready = false;
-        {
-            Phase ph(h, TLSQ_PHASE_EIG);
-            // a 16-column block is enough while the rank estimate stays <= 10 (it must stay <= block - 2); widening
-            // the block needs an orthonormal 32-column basis, which the next full Jacobi provides
-            const int want_bw = svp_last <= 10 ? 16 : 32;
-            if (want_bw > cur_bw) { have_q = false; cur_bw = 32; }
-            const bool block_fits = cur_bw <= eig_fast_max_block(n);      // n > 256: only the 16-column block
-            if (fast_ok && have_q && block_fits) {
-                // dominant eigenpairs + certified count; the full Jacobi below only runs (device-side flag) when the
-                // fast path could not prove the count
-                CK(launch_eig_fast(G, n, im, nukeA, fw, lam, Vs, sigma, fvec, dsvp, st, L, 0, cur_bw, si_budget));
-                CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
-                CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L, fw.flags));   // :198
-                CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
-                last_was_fast = true;
-            } else {
-                CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
-                CK(launch_svt_post(lam, n, im, nukeA, sigma, fvec, dsvp, st, L));        // :198
-                if (fast_ok) { CK(launch_copy_block(Vs, n, fw.Qb, nullptr, st, L)); have_q = true; }
-                last_was_fast = false;
-            }
-        }
+        ahead_done = false;
+        eig_stale = false;
+        bool was_fast_k = last_was_fast;
         const double mu_next = fmin(mu * p.rho, mubar);                                  // :223
         int svp = 0;
-        if (use_w || fused) {
-            // the streaming / fused kernels are specialised on the rank: fetch svp now (one short extra host sync)
+        // The streaming / fused kernels are specialised on the rank.  Two-kernel pipeline: launch on a guess (the last
+        // rank seen) and let the kernels check it; first iteration and the one-pass pipeline: fetch svp (short host sync).
+        bool svp_known = false;
+        int svp_guess = svp_last;
+        const bool speculate = use_w && !no_ahead && k > 1;
+        if ((use_w || fused) && !speculate) {
             CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
-            if (fast_ok && last_was_fast) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             memcpy(&svp, hp + 1, 4);
-            if (fast_ok && last_was_fast) {
-                int fl[4];
-                memcpy(fl, hp + 8, 16);
-                // converged in fl[3] steps: budget that + 3 next time; a fallback resets the budget
-                si_budget = fl[1] ? 12 : fl[3] + 3;
-            }
+            svp_known = true;
+            svp_guess = svp;
         }
         // will the Frobenius bracket [fro/sqrt(d), fro] probably straddle tol?  (fro shrinks by < 8x per iteration)
         bool want_z = (use_w || fused) && (exact_cost || (p.tol > 0.0 && prev_fro < 8.0 * sqrt(dmin) * p.tol));
@@ -541,6 +580,9 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
                 const double ratio = fmin(prev_fro / prev_prev_fro, 1.0);
                 want_z = prev_fro * ratio < 4.0 * sqrt(dmin) * p.tol;
             }
+            static const bool no_pred = getenv("TLSQ_NO_PREDICT_Z") != nullptr;     // test hook: exercise the retry below
+            if (inplace_y && no_pred && !exact_cost) want_z = false;
+            if (inplace_y && k >= two_phase_from) want_z = true;
         }
         if (fused && (svp > kFusedMaxRank || svpb[cur] > kFusedMaxRank)) {
             // rank estimate beyond the fused kernel: materialise W_k once and continue on the streaming pipeline
@@ -580,65 +622,122 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             } else {
                 Phase ph(h, TLSQ_PHASE_FUSED);
                 f.gram_of = FUSED_GRAM_WNEXT; f.compute_T = 1; f.write_Y = 1;
-                CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], nullptr, G, G + (size_t)n * n, sms, st, L));
-                CKR(allreduce(h, G, (size_t)n * n + 1, kNcclSum));
-                CK(cudaMemcpyAsync(hp, G + (size_t)n * n, 8, cudaMemcpyDeviceToHost, st));
+                CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], nullptr, Gnext, Gnext + (size_t)n * n, sms, st, L));
+                CKR(allreduce(h, Gnext, (size_t)n * n + 1, kNcclSum));
+                CK(cudaMemcpyAsync(hp, Gnext + (size_t)n * n, 8, cudaMemcpyDeviceToHost, st));
                 gram_ready = true;
             }
             CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
             svpb[nxt] = svp;
+            CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
+            if (dbg_eig) {
+                CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
+                if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
+            }
+            if (fast_ok && was_fast_k) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
         } else {
             // ---- epilogue of the two-kernel pipelines  (:188-192, 205-222) -----------------------------------------
-            CK(cudaMemsetAsync(dscal, 0, 8, st));
-            ea.D = D; ea.Ap = Abuf[cur]; ea.Yp = Ybuf[cur]; ea.An = Abuf[nxt]; ea.Yn = Ybuf[nxt];
-            ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
-            ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
-            ea.zz = dscal;
-            if (want_z && !Zbuf && !inplace_y) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
-            ea.Zout = (want_z && Zbuf) ? Zbuf : nullptr;
-            ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
-            {
-                Phase ph(h, TLSQ_PHASE_EPILOGUE);
-                if (fact && !stream_factored_fits(N, svp, svpb[cur])) {
-                    // rank estimate beyond the factored kernels: materialise A_{k-1} and continue with the dense iterate
-                    CK(alloc_dense_a());
-                    CK(launch_fact_to_dense(Tb[cur], Vb[cur], svpb[cur], M, N, nonnegA, Abuf[cur], sms, st, L));
-                    ea.Ap = Abuf[cur]; ea.An = Abuf[nxt];
-                    fact = false;
+            for (int attempt = 0;; ++attempt) {
+                CK(cudaMemsetAsync(dscal, 0, 8, st));
+                ea = EpiArgs{};
+                ea.D = D; ea.Ap = Abuf[cur]; ea.Yp = Ybuf[cur]; ea.An = Abuf[nxt]; ea.Yn = Ybuf[nxt];
+                ea.Eout = nullptr; ea.Uout = nullptr; ea.M = M; ea.N = N; ea.ldw = M; ea.Vs = Vs; ea.fvec = fvec;
+                ea.svp = dsvp; ea.im = im; ea.eps = eps; ea.mu = mu; ea.nonnegA = nonnegA; ea.nonnegE = nonnegE;
+                ea.zz = dscal;
+                if (want_z && !Zbuf && !inplace_y) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
+                ea.Zout = (want_z && Zbuf) ? Zbuf : nullptr;
+                ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
+                bool guarded = false;          // the launch below checks the rank guess on the device
+                int rp_launched = 0;
+                {
+                    Phase ph(h, TLSQ_PHASE_EPILOGUE);
+                    if (fact && !stream_factored_fits(N, svp_guess, svpb[cur])) {
+                        // rank estimate beyond the factored kernels: materialise A_{k-1} and continue with the dense iterate
+                        CK(alloc_dense_a());
+                        CK(launch_fact_to_dense(Tb[cur], Vb[cur], svpb[cur], M, N, nonnegA, Abuf[cur], sms, st, L));
+                        ea.Ap = Abuf[cur]; ea.An = Abuf[nxt];
+                        fact = false;
+                    }
+                    if (fact) {
+                        ea.Tp = Tb[cur]; ea.Vp = Vb[cur]; ea.svp_prev = svpb[cur]; ea.Tn = Tb[nxt];
+                        CK(launch_stream_epilogue(ea, Wbuf, svp_guess, hankel, sms, st, L, !svp_known));
+                        guarded = !svp_known;
+                        rp_launched = stream_rank_pad(svp_guess, svpb[cur], true);
+                        // V_k of this iterate (Vs is overwritten by the next eigen-decomposition)
+                        CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
+                    } else if (use_w && svp_guess <= kStreamMaxRank) {
+                        CK(launch_stream_epilogue(ea, Wbuf, svp_guess, hankel, sms, st, L, !svp_known));
+                        guarded = !svp_known;
+                        rp_launched = stream_rank_pad(svp_guess, 0, false);
+                    } else if (hk) {
+                        // A_raw = U_r (S_r - 1/mu) V_r' ; soft_hankel!(A, lambda/mu) ; clamp ; Z ; Y   (:205-222)
+                        ea.raw_only = 1;
+                        CK(launch_epilogue(ea, hankel, false, sms, st, L));
+                        CK(launch_unhankel(ea.An, M, N, 1, M + N - 1, meanbuf, st, L));          // anti-diagonal means
+                        CK(launch_hankel_finish(ea, hankel, meanbuf, sms, st, L));
+                    } else {
+                        CK(launch_epilogue(ea, hankel, false, sms, st, L));
+                    }
                 }
-                if (fact) {
-                    ea.Tp = Tb[cur]; ea.Vp = Vb[cur]; ea.svp_prev = svpb[cur]; ea.Tn = Tb[nxt];
-                    CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
-                    // V_k of this iterate (Vs is overwritten by the next eigen-decomposition)
-                    CK(cudaMemcpyAsync(Vb[nxt], Vs, (size_t)N * kStreamMaxRank * 8, cudaMemcpyDeviceToDevice, st));
-                    svpb[nxt] = svp;
-                } else if (use_w && svp <= kStreamMaxRank) {
-                    CK(launch_stream_epilogue(ea, Wbuf, svp, hankel, sms, st, L));
-                } else if (hk) {
-                    // A_raw = U_r (S_r - 1/mu) V_r' ; soft_hankel!(A, lambda/mu) ; clamp ; Z ; Y   (:205-222)
-                    ea.raw_only = 1;
-                    CK(launch_epilogue(ea, hankel, false, sms, st, L));
-                    CK(launch_unhankel(ea.An, M, N, 1, M + N - 1, meanbuf, st, L));          // anti-diagonal means
-                    CK(launch_hankel_finish(ea, hankel, meanbuf, sms, st, L));
+                CKR(allreduce(h, dscal, 1, kNcclSum));
+                CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
+                if (dbg_eig) {
+                    CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
+                    if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
+                }
+                if (fast_ok && was_fast_k) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
+                // run-ahead: Gram + eigen step of iteration k+1 behind the epilogue, before the host looks at the result
+                const bool run_ahead = use_w && !no_ahead && !want_z && k < p.iters && attempt == 0;
+                if (run_ahead) {
+                    CK(cudaEventRecord(h->ev_iter, st));
+                    {
+                        Phase ph(h, TLSQ_PHASE_GRAM);
+                        CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), Gnext, st, L));
+                    }
+                    CKR(allreduce(h, Gnext, (size_t)n * n, kNcclSum));
+                    CKR(enqueue_eig(Gnext, 1.0 / mu_next));
+                    ahead_done = true;
+                    eig_stale = true;
+                    CK(cudaEventSynchronize(h->ev_iter));
                 } else {
-                    CK(launch_epilogue(ea, hankel, false, sms, st, L));
+                    CK(cudaStreamSynchronize(st));
                 }
+                int svp_dev = 0;
+                memcpy(&svp_dev, hp + 1, 4);
+                if (guarded && svp_dev > rp_launched) {
+                    // the guess was too small: the epilogue kernels returned without touching anything.  A run-ahead
+                    // eigen step has overwritten this iteration's sigma / V_r: redo it from the intact Gram.
+                    ++n_redo;
+                    if (ahead_done) {
+                        CKR(enqueue_eig(G, im));
+                        was_fast_k = last_was_fast;
+                        ahead_done = false;
+                        eig_stale = false;
+                    }
+                    svp_guess = svp_dev;
+                    svp_known = true;
+                    continue;
+                }
+                svp = svp_dev;
+                break;
             }
-            CKR(allreduce(h, dscal, 1, kNcclSum));
-            CK(cudaMemcpyAsync(hp, dscal, 8, cudaMemcpyDeviceToHost, st));
+            if (fact) svpb[nxt] = svp;
         }
-        CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
-        if (dbg_eig) {
-            CK(cudaMemcpyAsync(hp + 2, ew.info, 4, cudaMemcpyDeviceToHost, st));
-            if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
+        if (fast_ok && was_fast_k) {
+            int fl[4];
+            memcpy(fl, hp + 8, 16);
+            // converged in fl[3] steps: budget that + 3 next time; a fallback resets the budget
+            si_budget = fl[1] ? 12 : fl[3] + 3;
         }
-        CK(cudaStreamSynchronize(st));
         if (dbg_eig) {
             int sw, fl[8] = {0};
             memcpy(&sw, hp + 2, 4);
             if (fast_ok) memcpy(fl, hp + 4, 32);
             fprintf(stderr, "[tlsq] iter %lld: full-jacobi sweeps %d | fast: conv %d need_full %d svp %d si_steps %d "
-                            "certified %d si_sweeps %d\n", (long long)k, sw, fl[0], fl[1], fl[2], fl[3], fl[4], fl[5]);
+                            "certified %d si_sweeps %d | redo %lld ahead %d\n", (long long)k, sw, fl[0], fl[1], fl[2], fl[3],
+                    fl[4], fl[5], (long long)n_redo, ahead_done ? 1 : 0);
         }
         zz = hp[0];
         memcpy(&svp, hp + 1, 4);
@@ -657,10 +756,12 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
         prev_prev_fro = prev_fro;
         prev_fro = fro;
         if (need_exact && inplace_y && !z_gram_ready) {
-            // Y was updated in place and the bracket was not predicted: Z_k cannot be rebuilt.  Only the upper bound
-            // is available -> not converged (at worst one more iteration than the reference).
-            need_exact = false;
-            converged = false;
+            // Y was updated in place and the prediction missed an undecided Frobenius bracket: Z_k cannot be rebuilt from
+            // Y_k alone.  The solve is deterministic and D is never modified, so it is simply repeated with the two-phase
+            // iteration forced from this iteration on -- the stopping iteration always equals the reference's (:225-231).
+            *escape_at = k;
+            CK(cudaStreamSynchronize(st));
+            return kRetryTwoPhase;
         }
         if (need_exact) {
             Phase ph(h, TLSQ_PHASE_EXACT_COST);
@@ -679,6 +780,7 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             } else if (fact) {
                 // the bracket was not predicted: rebuild Z_k from the factored iterates, then the same SYRK
                 if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
+                ea.Vs = Vb[nxt];               // V_k (Vs may already belong to the run-ahead eigen step)
                 CK(launch_z_from_factors(ea, hankel, svp, Zbuf, sms, st, L));
                 CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
                 CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
@@ -719,122 +821,105 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
             f.Yn = Ybuf[nxt]; f.Tn = nullptr;
             f.im = im; f.eps = eps; f.mu = mu; f.im_next = 1.0 / mu_next; f.eps_next = p.lambda / mu_next;
             f.gram_of = FUSED_GRAM_WNEXT; f.compute_T = 0; f.write_Y = 1;
-            CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], Tb[nxt], G, nullptr, sms, st, L));
-            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
+            CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], Tb[nxt], Gnext, nullptr, sms, st, L));
+            CKR(allreduce(h, Gnext, (size_t)n * n, kNcclSum));
             gram_ready = true;
         }
         mu = mu_next;
         cur = nxt;
         if (converged) { conv = 1; break; }
+        if (k == p.iters) break;
+        if (gram_ready || ahead_done) gi ^= 1;         // the next iteration's Gram is in the other buffer
     }
+    double* G = Gb[gi];                                // Gram of the LAST iteration's SVT input W_k
 
     // ---- outputs (:238) ----------------------------------------------------------------------------------
     Phase ph_final(h, TLSQ_PHASE_FINALIZE);
-    bool joined = true;
-    // fork point of the side stream (see below); the eigensolver is enqueued FIRST so that its cluster kernel gets its
-    // SMs before the bandwidth-bound output pass fills the machine
-    if (fact && o.U) CK(ensure_w());          // allocated in stream order BEFORE the fork point
+    const bool want_svd = o.S || o.Vt || o.U;
+    // The returned SVD is that of the LAST SVT input W_k (:194, 238): W_k is materialised once (the W buffer of the
+    // two-kernel pipeline is free now).
+    double* Wfin = nullptr;
+    if (want_svd) { CK(ensure_w()); Wfin = Wbuf; }           // allocated in stream order BEFORE the fork point
+    // fork point of the side stream; the eigensolver is enqueued FIRST so that its cluster kernel gets its SMs before
+    // the bandwidth-bound output pass fills the machine
     CK(cudaEventRecord(h->ev_fork, st));
-    if (fast_ok && last_was_fast && (o.S || o.Vt || o.U)) {
-        // the fast path only carries the dominant block; the returned SVD (:238) needs the full spectrum of the last W.
-        // On the fused path G already holds the Gram of W_{k+1}: rebuild W_k'W_k from (Y_{k-1}, T_{k-1}).
-        if (gram_ready) {
-            FusedArgs f = fa;
-            f.Vp = Vb[prev_idx]; f.svp_prev = svpb[prev_idx]; f.im = im_last; f.eps = eps_last;
-            f.gram_of = FUSED_GRAM_W;
-            CK(launch_alm_fused(f, hankel, Ybuf[prev_idx], Tb[prev_idx], nullptr, G, nullptr, sms, st, L));
-            CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
-        }
+    if (want_svd && (eig_stale || (fast_ok && last_was_fast))) {
+        // the fast path only carries the dominant block (and a run-ahead eigen step belongs to an iteration that never
+        // ran); the returned SVD needs the full spectrum of W_k, whose Gram is still in G
         CK(launch_eigh(G, n, nullptr, ew, lam, Vs, sms, st, L));
         CK(launch_svt_post(lam, n, im_last, nukeA, sigma, fvec, dsvp, st, L));
     }
     if (fact) {
-        // Factored iterate: ONE pass produces A_k, E_k and (for U) the last SVT input W_k from
-        // (T_{k-1}, V_{k-1}, Y_{k-1}) and (T_k, V_k); W_k lands in the W buffer, which is free now.  The pass is
-        // HBM-bound and independent of the full eigen-decomposition below (latency-bound, a few SMs): it runs on the
-        // side stream, concurrently.
+        // Factored iterate: ONE pass produces A_k, E_k and (for the SVD) W_k from (T_{k-1}, V_{k-1}, Y_{k-1}) and
+        // (T_k, V_k).  The pass is HBM-bound and independent of the full eigen-decomposition above (latency-bound, a few
+        // SMs): it runs on the side stream, concurrently.
         cudaStream_t ss = h->side;
         CK(cudaStreamWaitEvent(ss, h->ev_fork, 0));
         if (o.uh_sum)
             CK(launch_unhankel_factors(Tb[last_idx], ldp, Vb[last_idx], svpb[last_idx], nonnegA, o.uh_r0, M, N, o.uh_Ns,
                                        o.uh_sum, sms, ss, L));
-        if (o.E || o.U) {
+        if (o.E || want_svd) {
             EpiArgs fe = {};
             fe.D = D; fe.Yp = Ybuf[prev_idx]; fe.Tp = Tb[prev_idx]; fe.Vp = Vb[prev_idx]; fe.svp_prev = svpb[prev_idx];
             fe.Tn = Tb[last_idx]; fe.Vs = Vb[last_idx]; fe.An = o.A; fe.Eout = o.E; fe.M = M; fe.N = N; fe.ldw = M;
             fe.im = im_last; fe.eps = eps_last; fe.nonnegA = nonnegA; fe.nonnegE = nonnegE;
-            CK(launch_final_from_factors(fe, hankel, svpb[last_idx], o.U ? Wbuf : nullptr, sms, ss, L));
+            CK(launch_final_from_factors(fe, hankel, svpb[last_idx], Wfin, sms, ss, L));
         } else if (o.A) {
             CK(launch_fact_to_dense(Tb[last_idx], Vb[last_idx], svpb[last_idx], M, N, nonnegA, o.A, sms, ss, L));
         }
         CK(cudaEventRecord(h->ev_join, ss));
-        joined = false;
-    }
-    if (!joined) { CK(cudaStreamWaitEvent(st, h->ev_join, 0)); joined = true; }
-    if (fact) {
-        if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-        if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
-        if (o.U) {
-            // U = W_k V diag(1/s): DMMA GEMM (gemm.cu); odd shapes take the fused tile kernel on a dense A_{k-1}
-            if (gemm_xb_eligible(Wbuf, M, n, M, n)) {
-                CK(launch_scale_cols_inv(Vs, sigma, n, sqA, st, L));
-                CK(launch_gemm_xb(Wbuf, M, n, M, sqA, n, o.U, st, L));
-            } else {
-                if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
-                CK(launch_fact_to_dense(Tb[prev_idx], Vb[prev_idx], svpb[prev_idx], M, N, nonnegA, Zbuf, sms, st, L));
-                std::vector<double> hs(n);
-                CK(cudaMemcpyAsync(hs.data(), sigma, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
-                CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-                CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
-                EpiArgs eu = {};
-                eu.D = D; eu.Ap = Zbuf; eu.Yp = Ybuf[prev_idx]; eu.Uout = o.U; eu.M = M; eu.N = N; eu.ldw = M;
-                eu.Vs = Vs; eu.fvec = fvec; eu.svp = dsvp; eu.im = im_last; eu.eps = eps_last;
-                eu.nonnegA = nonnegA; eu.nonnegE = nonnegE; eu.zz = dscal;
-                CK(launch_epilogue(eu, hankel, true, sms, st, L));
+        CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    } else {
+        if (o.uh_sum) {
+            // the rank estimate left the factored path: anti-diagonal sums from the dense A_k
+            DevBuf bCnt;
+            CK(bCnt.alloc((size_t)o.uh_Ns * 8, st));
+            CK(cudaMemsetAsync(o.uh_sum, 0, (size_t)o.uh_Ns * 8, st));
+            CK(launch_unhankel_partial(Abuf[last_idx], o.uh_r0, M, N, 1, o.uh_Ns, o.uh_sum, bCnt.as<double>(), st, L));
+        }
+        // NB: E and W_k are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must
+        // be produced before A_k is copied there.
+        if (o.E || want_svd) {
+            CK(launch_compute_e(D, hankel, M, N, Abuf[prev_idx], Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
+                                st, L, Wfin));
+            if (hk && o.E) {                                                             // soft_hankel!(E, lambda/mu) :234-236
+                CK(launch_unhankel(o.E, M, N, 1, M + N - 1, meanbuf, st, L));
+                CK(launch_soft_hankel_apply(o.E, M, N, meanbuf, p.lambda / mu, sms, st, L));
             }
         }
-    } else {
-    if (o.uh_sum) {
-        // the rank estimate left the factored path: anti-diagonal sums from the dense A_k
-        DevBuf bCnt;
-        CK(bCnt.alloc((size_t)o.uh_Ns * 8, st));
-        CK(cudaMemsetAsync(o.uh_sum, 0, (size_t)o.uh_Ns * 8, st));
-        CK(launch_unhankel_partial(Abuf[last_idx], o.uh_r0, M, N, 1, o.uh_Ns, o.uh_sum, bCnt.as<double>(), st, L));
+        if (o.A && Abuf[last_idx] != o.A)
+            CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
     }
-    // NB: E and U are recomputed from (A_{k-1}, Y_{k-1}); A_{k-1} may live in the caller's A buffer, so they must be
-    // produced before A_k is copied there.
-    const double* Aprev_dense = Abuf[prev_idx];
-    if (o.E)
-    {
-        CK(launch_compute_e(D, hankel, M, N, Aprev_dense, Ybuf[prev_idx], im_last, eps_last, nonnegE, o.E, sms,
-                            st, L));
-        if (hk) {                                                                        // soft_hankel!(E, lambda/mu) :234-236
-            CK(launch_unhankel(o.E, M, N, 1, M + N - 1, meanbuf, st, L));
-            CK(launch_soft_hankel_apply(o.E, M, N, meanbuf, p.lambda / mu, sms, st, L));
+    if (want_svd) {
+        // SVD refinement (CholeskyQR2 with the eigenvectors of the Gram as the first factor).  sigma, V from
+        // eig(W'W) carry an absolute error eps*s_1^2/s_i, visible in the tail of the spectrum.  With s~ = max(s, 1e-8 s_1):
+        //   C = W V diag(1/s~)            nearly orthonormal columns (DMMA GEMM)
+        //   C'C = R'R                     Gram formed FROM THE DATA in the rotated, scaled basis + Cholesky
+        //   K = R diag(s~) = U_K S V_K'   one-sided Jacobi of the n x n factor: K'K = V' W'W V exactly (to eps kappa(C)^2)
+        //   W = (W V V_K S^-1) S (V V_K)' singular values to eps*s_1 like LAPACK's, V = V V_K, U = W V S^-1
+        static const bool no_refine = getenv("TLSQ_NO_SVD_REFINE") != nullptr;
+        double* Vfin = Vs;
+        if (!no_refine) {
+            double* Cbuf = o.U;
+            if (!Cbuf) { if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); } Cbuf = Zbuf; }
+            double* sc = lam2;                       // clamped scales s~
+            double* Gn2 = Gb[gi ^ 1];                // free n x n scratch
+            CK(launch_scale_cols_floor(Vs, sigma, n, 1.0e-8, sqA, sc, st, L));
+            CK(launch_gemm_any(Wfin, M, n, M, sqA, n, Cbuf, st, L));
+            CKR(gram_dense(h, Cbuf, M, n, G2));
+            CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
+            CK(launch_chol_upper(G2, n, st, L));
+            CK(launch_scale_cols_mul(G2, sc, n, sqB, st, L));
+            CK(launch_eigh(sqB, n, nullptr, ew, sigma, Vs2, sms, st, L, nullptr, 1));
+            CK(launch_gemm_nn(Vs, Vs2, n, Gn2, st, L));
+            Vfin = Gn2;
         }
-    }
-    if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-    if (o.Vt) CK(launch_transpose(Vs, N, N, o.Vt, st, L));
-    if (o.U) {
-        // U[:, c] = W v_c / s_c  with W the last SVT input (recomputed from A_{k-1}, Y_{k-1})
-        std::vector<double> hs(n);
-        CK(cudaMemcpyAsync(hs.data(), sigma, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        for (int i = 0; i < n; ++i) hs[i] = hs[i] > 0.0 ? 1.0 / hs[i] : 0.0;
-        CK(cudaMemcpyAsync(fvec, hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dsvp, &n, 4, cudaMemcpyHostToDevice, st));
-        EpiArgs eu = {};
-        eu.D = D; eu.Ap = Aprev_dense; eu.Yp = Ybuf[prev_idx]; eu.An = nullptr; eu.Yn = nullptr;
-        eu.Wn = nullptr; eu.im_next = 0.0; eu.eps_next = 0.0; eu.Zout = nullptr;
-        eu.Eout = nullptr; eu.Uout = o.U; eu.M = M; eu.N = N; eu.ldw = M; eu.Vs = Vs; eu.fvec = fvec;
-        eu.svp = dsvp; eu.im = im_last; eu.eps = eps_last; eu.mu = 0.0; eu.nonnegA = nonnegA; eu.nonnegE = nonnegE;
-        eu.zz = dscal;
-        CK(launch_epilogue(eu, hankel, true, sms, st, L));
-    }
-    if (o.A && Abuf[last_idx] != o.A)
-        CK(cudaMemcpyAsync(o.A, Abuf[last_idx], mn * 8, cudaMemcpyDeviceToDevice, st));
+        if (o.S) CK(cudaMemcpyAsync(o.S, sigma, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        if (o.Vt) CK(launch_transpose(Vfin, N, N, o.Vt, st, L));
+        if (o.U) {
+            CK(launch_scale_cols_inv(Vfin, sigma, n, sqA, st, L));
+            CK(launch_gemm_any(Wfin, M, n, M, sqA, n, o.U, st, L));                      // U = W_k V diag(1/s)
+        }
     }
     CK(cudaStreamSynchronize(st));
     if (o.sv) {
@@ -846,6 +931,17 @@ int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const
     if (o.iters_done) *o.iters_done = k_done;
     if (o.converged) *o.converged = conv;
     return TLSQ_OK;
+}
+
+int rpca_core(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, const RpcaParams& p, const RpcaOut& o) {
+    int64_t two_phase_from = INT64_MAX;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        int64_t escape_at = 0;
+        const int r = rpca_core_once(h, D, hankel, M, N, p, o, two_phase_from, &escape_at);
+        if (r != kRetryTwoPhase) return r;
+        two_phase_from = escape_at;
+    }
+    return set_err(TLSQ_ERR_CUDA, "rpca: internal error (two-phase retry did not settle)");
 }
 
 int check_rpca_args(int64_t M, int64_t N, const RpcaParams& p) {
@@ -1183,12 +1279,22 @@ int tlsq_create(int device, tlsq_handle** out) {
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_iter, cudaEventDisableTiming));
     CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double)));
-    // keep freed blocks cached in the stream-ordered pool between solves
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // keep freed blocks cached between solves -- in a pool of our own (the default pool's attributes are left alone)
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        } else {
+            cudaGetLastError();
+            h->pool = nullptr;               // fall back to the default pool, untouched
+        }
     }
     *out = h;
     return TLSQ_OK;
@@ -1202,7 +1308,9 @@ int tlsq_destroy(tlsq_handle* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_iter) cudaEventDestroy(h->ev_iter);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); if (t_pool == h->pool) t_pool = nullptr; }
     delete h;
     return TLSQ_OK;
 }
@@ -1282,7 +1390,8 @@ int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double 
     if (M < 1 || N < 1) return set_err(TLSQ_ERR_ARG, "rpca: empty matrix");
     cudaStream_t st = h->stream;
     const size_t mn = (size_t)M * N;
-    const int64_t d = M < N ? M : N;      // (sharded callers use the _dev entry; here M is the full row count)
+    // thin-SVD width d = min(M_global, N); a row shard (communicator attached) always has M_global >= N (rpca_core)
+    const int64_t d = (h->nranks > 1) ? N : (M < N ? M : N);
     DevBuf bD, bA, bE, bU, bS, bVt;
     CK(bD.alloc(mn * 8, st));
     CK(cudaMemcpyAsync(bD.as<double>(), D, mn * 8, cudaMemcpyHostToDevice, st));
@@ -1358,6 +1467,7 @@ int tlsq_rpca_ga_mu_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t 
     CKR(use_device(h));
     if (mu_kind < 0 || mu_kind > 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: mu_kind must be 0 (mean), 1 (trimmed mean) or 2 (median)");
     if (mu_kind && N > 1024) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most 1024 observations");
+    if (mu_kind == 2 && N < 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: entrywise_median needs at least 2 observations (I[end / 2], src/robustPCA.jl:353)");
     return rpca_ga_dev(h, X, d, N, r, q0, tol, iters, Q, iters_done, mu_kind, mu_p);
 }
 
@@ -1367,6 +1477,7 @@ int tlsq_rpca_ga_mu_f64(tlsq_handle* h, const double* X, int64_t d, int64_t N, i
     if (!X || !q0 || !Q || d < 1 || N < 1 || r < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: bad arguments");
     if (mu_kind < 0 || mu_kind > 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: mu_kind must be 0 (mean), 1 (trimmed mean) or 2 (median)");
     if (mu_kind && N > 1024) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most 1024 observations");
+    if (mu_kind == 2 && N < 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: entrywise_median needs at least 2 observations (I[end / 2], src/robustPCA.jl:353)");
     cudaStream_t st = h->stream;
     DevBuf bX, bq0, bQ;
     CK(bX.alloc((size_t)d * N * 8, st)); CK(bq0.alloc((size_t)d * r * 8, st)); CK(bQ.alloc((size_t)d * r * 8, st));

@@ -36,7 +36,12 @@ __device__ __forceinline__ double dot_rp(const double (&t)[RP > 0 ? RP : 1], con
 // back from a.Tn).  The split form (1 then 2, FACT only) runs each loop at a higher occupancy.
 template <int RP, bool HANKEL, bool FACT, int PH>
 __global__ void __launch_bounds__(128)
-alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp) {
+alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp_host, const int* __restrict__ svp_dev) {
+    // Rank of this iteration: either known on the host, or (speculative launch, solver.cu) read from the device scalar
+    // the eigen step just wrote.  The launch was specialised on a GUESS of the rank; if the actual rank does not fit
+    // the guess the whole grid returns before touching anything and the host relaunches with the right RP.
+    const int svp = svp_dev ? __ldg(svp_dev) : svp_host;
+    if (svp > RP) return;
     extern __shared__ double Vsm[];            // [N][RP]  (+ [N][RP] of V_{k-1} when FACT)
     __shared__ double fsm[RP > 0 ? RP : 1];
     const int N = (int)a.N;
@@ -220,7 +225,8 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
 inline int rp_of(int svp) { return svp <= 16 ? ((svp + 3) & ~3) : ((svp + 7) & ~7); }
 
 template <int RP>
-cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count, cudaStream_t st) {
+cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, const int* svp_dev, bool hankel, int sm_count,
+                             cudaStream_t st) {
     const bool fact = a.Tn != nullptr;
     static const bool split_env = getenv("TLSQ_STREAM_SPLIT") ? atoi(getenv("TLSQ_STREAM_SPLIT")) != 0 : true;
     const bool split = fact && split_env && RP > 0;
@@ -234,7 +240,7 @@ cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, bool ha
         auto kern = alm_stream_kernel<RP, H, F, PH>;                                                              \
         const size_t smem_ = (SM);                                                                                \
         if (smem_ > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
-        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem_, st>>>(a, W, svp);                              \
+        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem_, st>>>(a, W, svp, svp_dev);                     \
     } while (0)
     const size_t sm1 = (size_t)a.N * RP * sizeof(double);
     if (split) {
@@ -280,21 +286,24 @@ bool stream_factored_fits(int64_t N, int svp, int svp_prev) {
     return (size_t)N * rp * 8 * 2 <= (size_t)200 * 1024;
 }
 
+int stream_rank_pad(int svp, int svp_prev, bool fact) { return rp_of(fact && svp_prev > svp ? svp_prev : svp); }
+
 cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count,
-                                   cudaStream_t st, int64_t* launches) {
+                                   cudaStream_t st, int64_t* launches, bool svp_on_device) {
     cudaError_t e;
     const bool fact = a.Tn != nullptr;
     const int rp = rp_of(fact && a.svp_prev > svp ? a.svp_prev : svp);
+    const int* svp_dev = svp_on_device ? a.svp : nullptr;
     switch (rp) {
-        case 0:  e = launch_stream_rp<0>(a, W, svp, hankel, sm_count, st); break;
-        case 4:  e = launch_stream_rp<4>(a, W, svp, hankel, sm_count, st); break;
-        case 8:  e = launch_stream_rp<8>(a, W, svp, hankel, sm_count, st); break;
-        case 12: e = launch_stream_rp<12>(a, W, svp, hankel, sm_count, st); break;
-        case 16: e = launch_stream_rp<16>(a, W, svp, hankel, sm_count, st); break;
-        case 24: e = launch_stream_rp<24>(a, W, svp, hankel, sm_count, st); break;
-        default: e = launch_stream_rp<32>(a, W, svp, hankel, sm_count, st); break;
+        case 0:  e = launch_stream_rp<0>(a, W, svp, svp_dev, hankel, sm_count, st); break;
+        case 4:  e = launch_stream_rp<4>(a, W, svp, svp_dev, hankel, sm_count, st); break;
+        case 8:  e = launch_stream_rp<8>(a, W, svp, svp_dev, hankel, sm_count, st); break;
+        case 12: e = launch_stream_rp<12>(a, W, svp, svp_dev, hankel, sm_count, st); break;
+        case 16: e = launch_stream_rp<16>(a, W, svp, svp_dev, hankel, sm_count, st); break;
+        case 24: e = launch_stream_rp<24>(a, W, svp, svp_dev, hankel, sm_count, st); break;
+        default: e = launch_stream_rp<32>(a, W, svp, svp_dev, hankel, sm_count, st); break;
     }
-    if (launches) *launches += 1;
+    if (launches) *launches += (fact && rp > 0) ? 2 : 1;
     return e;
 }
 
