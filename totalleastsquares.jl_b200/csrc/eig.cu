@@ -415,6 +415,63 @@ jacobi_global_kernel(int n, int np, double tol, int max_sweeps, double* __restri
     if (gw == 0 && lane == 0) info[0] = sweep;
 }
 
+
+// Same engine for large n (> 512): a column no longer fits a lane's registers, so every pair makes two passes over its
+// columns (dot products, then the rotation) out of L2.  Slow (O(100 ms) per sweep at n = 2048) but it is only the
+// fallback of the large-n fast path and the once-per-solve full spectrum of the returned SVD.
+__global__ void __launch_bounds__(256)
+jacobi_global_loop_kernel(int n, int np, double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
+                          int* __restrict__ info, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int npairs = np / 2;
+    int* counters = info + 2;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        bool rotated = false;
+        for (int round = 0; round < np - 1; ++round) {
+            for (int pi = gw; pi < npairs; pi += nw) {
+                int p, q;
+                if (pi == 0) { p = np - 1; q = round; }
+                else { p = (round + pi) % (np - 1); q = (round - pi + (np - 1)) % (np - 1); }
+                if (p >= n || q >= n) continue;
+                double* xp = Xo + (int64_t)p * n;
+                double* xq = Xo + (int64_t)q * n;
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    const double a = __ldcg(xp + i), b = __ldcg(xq + i);
+                    alpha = fma(a, a, alpha);
+                    beta = fma(b, b, beta);
+                    gamma = fma(a, b, gamma);
+                }
+                alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+                double c, s;
+                if (!jacobi_cs(alpha, beta, gamma, tol, c, s)) continue;
+                rotated = true;
+                double* vp = Vo + (int64_t)p * n;
+                double* vq = Vo + (int64_t)q * n;
+                for (int i = lane; i < n; i += 32) {
+                    const double a = __ldcg(xp + i), b = __ldcg(xq + i);
+                    __stcg(xp + i, fma(c, a, -s * b));
+                    __stcg(xq + i, fma(s, a, c * b));
+                    const double va = __ldcg(vp + i), vb = __ldcg(vq + i);
+                    __stcg(vp + i, fma(c, va, -s * vb));
+                    __stcg(vq + i, fma(s, va, c * vb));
+                }
+            }
+            grid.sync();
+        }
+        if (rotated && lane == 0) atomicAdd(counters + sweep, 1);
+        grid.sync();
+        const int cnt = *((volatile int*)(counters + sweep));
+        if (cnt == 0) { ++sweep; break; }
+    }
+    if (gw == 0 && lane == 0) info[0] = sweep;
+}
+
 // prepare Xo/Vo for the global engine: Xo = X0 (or G), Vo = V0 (or I)
 __global__ void jacobi_global_init_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n,
                                           double* __restrict__ Xo, double* __restrict__ Vo, int* __restrict__ info,
@@ -605,6 +662,7 @@ cudaError_t launch_global(int n, int np, double tol, int max_sweeps, double* Xo,
     if (blocks > sm_count) blocks = sm_count;
     if (blocks < 1) blocks = 1;
     void* args[] = {&n, &np, &tol, &max_sweeps, &Xo, &Vo, &info, &run_flag};
+    if (n > 32 * E) return cudaLaunchCooperativeKernel((void*)jacobi_global_loop_kernel, dim3(blocks), dim3(256), args, 0, st);
     return cudaLaunchCooperativeKernel((void*)jacobi_global_kernel<E>, dim3(blocks), dim3(256), args, 0, st);
 }
 

@@ -391,15 +391,266 @@ cudaError_t launch_si(const double* X, double* Q, int n, double tau2, int min_wa
     return cudaGetLastError();
 }
 
+
+// =====================================================================================================================
+// Large embeddings (512 < n <= 2048): the same algorithm with the block kept in global memory (L2 resident) and the
+// Rayleigh-Ritz step done on the 32 x 32 projected matrix.  One step, given an orthonormal n x 32 basis Q:
+//   X = G Q (DMMA)            H = Q'X (32 x 32)            H = R Theta R'  (one-sided Jacobi, one CTA, registers)
+//   Q~ = Q R, X~ = X R        r_i = |x~_i - theta_i q~_i|  (Ritz pairs and residuals)
+//   converged (all wanted pairs)  ->  Qout = Q~, theta;    else Q <- orth(X~) by CholeskyQR2 on the normalised columns
+// followed by the same deflation + squaring certificate of the count as the small path.  All kernels look at the device
+// flags themselves, so the host enqueues a fixed number of steps without a round trip.
+// =====================================================================================================================
+constexpr int LB = 32;
+
+__global__ void __launch_bounds__(16 * LB, 1)
+rr_small_eig_kernel(const double* __restrict__ H, double* __restrict__ theta, double* __restrict__ R,
+                    const int* __restrict__ flags) {
+    if (flags[0] == 1 || flags[1] == 1) return;
+    __shared__ double sm[LB * 2 * LB];              // slot c: [X part (32) | V part (32)]
+    __shared__ double th[LB];
+    __shared__ int order[LB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int m = LB / 2;
+    double xp[1], xq[1], vp[1], vq[1];
+    {
+        const int cp = 2 * warp, cq = 2 * warp + 1;
+        xp[0] = 0.5 * (H[cp * LB + lane] + H[lane * LB + cp]);      // symmetrised
+        xq[0] = 0.5 * (H[cq * LB + lane] + H[lane * LB + cq]);
+        vp[0] = lane == cp ? 1.0 : 0.0;
+        vq[0] = lane == cq ? 1.0 : 0.0;
+    }
+    const double tol = 1.0e-15 * 6.0;
+    for (int sweeps = 0; sweeps < 30; ++sweeps) {
+        int rotated = 0;
+        for (int round = 0; round < 2 * m - 1; ++round) {
+            rotated |= rotate_pair<1>(xp, xq, vp, vq, tol, 0.0) ? 1 : 0;
+            const int s = warp;
+            int ts, tw, bs, bw;
+            if (s == 0) { ts = 0; tw = 0; } else if (s == m - 1) { ts = m - 1; tw = 1; } else { ts = s + 1; tw = 0; }
+            if (s == 0) { bs = 1; bw = 0; } else { bs = s - 1; bw = 1; }
+            double* dt = sm + (size_t)(2 * ts + tw) * 2 * LB;
+            double* db = sm + (size_t)(2 * bs + bw) * 2 * LB;
+            dt[lane] = xp[0]; dt[LB + lane] = vp[0];
+            db[lane] = xq[0]; db[LB + lane] = vq[0];
+            __syncthreads();
+            const double* pt = sm + (size_t)(2 * s) * 2 * LB;
+            const double* pb = sm + (size_t)(2 * s + 1) * 2 * LB;
+            xp[0] = pt[lane]; vp[0] = pt[LB + lane];
+            xq[0] = pb[lane]; vq[0] = pb[LB + lane];
+            __syncthreads();
+        }
+        if (!__syncthreads_or(rotated)) break;
+    }
+    // eigenvalue of column c: v_c . x_c  (X = H V, V orthogonal)
+    {
+        const double dp = warp_sum(vp[0] * xp[0]);
+        const double dq = warp_sum(vq[0] * xq[0]);
+        if (lane == 0) { th[2 * warp] = dp; th[2 * warp + 1] = dq; }
+    }
+    __syncthreads();
+    if (tid < LB) {
+        const double lj = th[tid];
+        int rank = 0;
+        for (int k = 0; k < LB; ++k) rank += (th[k] > lj) || (th[k] == lj && k < tid);
+        order[tid] = rank;
+        theta[rank] = lj;
+    }
+    __syncthreads();
+    R[order[2 * warp] * LB + lane] = vp[0];
+    R[order[2 * warp + 1] * LB + lane] = vq[0];
+}
+
+// Qr = Q R, Xr = X R   (n x 32 times 32 x 32; thread <-> row)
+__global__ void __launch_bounds__(128)
+rr_rotate_kernel(const double* __restrict__ Q, const double* __restrict__ X, const double* __restrict__ R, int n,
+                 double* __restrict__ Qr, double* __restrict__ Xr, const int* __restrict__ flags) {
+    if (flags[0] == 1 || flags[1] == 1) return;
+    __shared__ double Rs[LB * LB];
+    for (int i = threadIdx.x; i < LB * LB; i += blockDim.x) Rs[i] = R[i];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q[LB], x[LB];
+#pragma unroll
+    for (int c = 0; c < LB; ++c) { q[c] = Q[(int64_t)c * n + i]; x[c] = X[(int64_t)c * n + i]; }
+#pragma unroll 4
+    for (int j = 0; j < LB; ++j) {
+        double aq = 0.0, ax = 0.0;
+#pragma unroll
+        for (int c = 0; c < LB; ++c) { aq = fma(q[c], Rs[j * LB + c], aq); ax = fma(x[c], Rs[j * LB + c], ax); }
+        Qr[(int64_t)j * n + i] = aq;
+        Xr[(int64_t)j * n + i] = ax;
+    }
+}
+
+// res[j] = |Xr_j - theta_j Qr_j|, nx[j] = |Xr_j|     (one CTA per column)
+__global__ void __launch_bounds__(256)
+rr_resid_kernel(const double* __restrict__ Qr, const double* __restrict__ Xr, const double* __restrict__ theta, int n,
+                double* __restrict__ res, double* __restrict__ nx, const int* __restrict__ flags) {
+    if (flags[0] == 1 || flags[1] == 1) return;
+    __shared__ double r1[8], r2[8];
+    const int j = blockIdx.x;
+    const double th = theta[j];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = Xr[(int64_t)j * n + i];
+        const double d = x - th * Qr[(int64_t)j * n + i];
+        a = fma(d, d, a);
+        b = fma(x, x, b);
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = a; r2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int w = 0; w < 8; ++w) { sa += r1[w]; sb += r2[w]; }
+        res[j] = sqrt(sa);
+        nx[j] = sqrt(sb);
+    }
+}
+
+// convergence decision of one step (same rules as si_jacobi_kernel) + outputs: converged -> Qout = Qr, theta_out;
+// otherwise the next (not yet orthonormal) basis Q = Xr with normalised columns.  Single CTA.
+__global__ void __launch_bounds__(1024)
+rr_decide_kernel(const double* __restrict__ Qr, const double* __restrict__ Xr, const double* __restrict__ theta,
+                 const double* __restrict__ res, const double* __restrict__ nx, int n, double tau2, int min_wanted,
+                 double tol_res, int last_step, double* __restrict__ Q, double* __restrict__ Qout,
+                 double* __restrict__ theta_out, int* __restrict__ flags) {
+    if (flags[0] == 1 || flags[1] == 1) return;
+    __shared__ int s_conv;
+    if (threadIdx.x == 0) {
+        int svp = 0;
+        for (int i = 0; i < LB; ++i) svp += (theta[i] >= tau2) ? 1 : 0;
+        if (svp < min_wanted) svp = min_wanted;
+        int conv = (svp <= LB - 2) ? 1 : 0;
+        const double lim = tol_res * fabs(theta[0]);
+        for (int i = 0; i < svp && i < LB; ++i) conv &= (res[i] <= lim) ? 1 : 0;
+        s_conv = conv;
+        flags[3] += 1;
+        if (conv) { flags[0] = 1; flags[2] = svp; }
+        else if (svp > LB - 2 || last_step) flags[1] = 1;
+    }
+    __syncthreads();
+    const int conv = s_conv;
+    if (conv) {
+        for (int idx = threadIdx.x; idx < n * LB; idx += blockDim.x) Qout[idx] = Qr[idx];
+        if (threadIdx.x < LB) theta_out[threadIdx.x] = theta[threadIdx.x];
+    } else {
+        for (int idx = threadIdx.x; idx < n * LB; idx += blockDim.x) {
+            const double nrm = nx[idx / n];
+            Q[idx] = nrm > 0.0 ? Xr[idx] / nrm : Qr[idx];
+        }
+    }
+}
+
+// Q <- Q Rc^-1 for an upper-triangular 32 x 32 Rc (row-wise forward substitution y Rc = x; a zero pivot zeroes the column)
+__global__ void __launch_bounds__(128)
+rr_trsm_kernel(double* __restrict__ Q, const double* __restrict__ Rc, int n, const int* __restrict__ flags) {
+    if (flags[0] == 1 || flags[1] == 1) return;
+    __shared__ double Rs[LB * LB];
+    for (int i = threadIdx.x; i < LB * LB; i += blockDim.x) Rs[i] = Rc[i];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double y[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+        double v = Q[(int64_t)j * n + i];
+#pragma unroll
+        for (int c = 0; c < LB; ++c)
+            if (c < j) v = fma(-y[c], Rs[j * LB + c], v);
+        const double d = Rs[j * LB + j];
+        y[j] = d > 0.0 ? v / d : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < LB; ++j) Q[(int64_t)j * n + i] = y[j];
+}
+
+// in-place upper Cholesky of the 32 x 32 Gram of the basis (single warp per column sweep; zero-pivot deflation)
+__global__ void __launch_bounds__(LB)
+rr_chol32_kernel(double* __restrict__ S, const int* __restrict__ flags) {
+    if (flags[0] == 1 || flags[1] == 1) return;
+    __shared__ double A[LB][LB + 1];               // A[i][k] = element (i, k), i <= k used
+    const int t = threadIdx.x;
+    for (int i = 0; i < LB; ++i) A[i][t] = S[t * LB + i];
+    __syncwarp();
+    const double d0 = A[t][t];
+    for (int j = 0; j < LB; ++j) {
+        const double ajj = A[j][j];
+        const double dj = __shfl_sync(0xffffffffu, d0, j);
+        const bool ok = ajj > 32.0 * 2.220446049250313e-16 * dj && dj > 0.0;
+        const double piv = ok ? sqrt(ajj) : 0.0;
+        const double ip = ok ? 1.0 / piv : 0.0;
+        __syncwarp();
+        double rjk = 0.0;
+        if (t >= j) { rjk = (t == j) ? piv : A[j][t] * ip; A[j][t] = rjk; }
+        __syncwarp();
+        if (ok && t > j)
+            for (int i = j + 1; i <= t; ++i) A[i][t] = fma(-A[j][i], rjk, A[i][t]);
+        __syncwarp();
+    }
+    for (int i = 0; i < LB; ++i) S[t * LB + i] = (i <= t) ? A[i][t] : 0.0;
+}
+
+cudaError_t launch_eig_large(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
+                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1,
+                             int max_steps) {
+    const int NSI = max_steps < 2 ? 2 : (max_steps > 16 ? 16 : max_steps);
+    constexpr int NSQ = 6;
+    cudaError_t e;
+    const double tau2 = top1 ? 1.0e300 : tau * tau;
+    const int min_wanted = top1 ? 1 : 0;
+    const double tol_res = 4.0e-14;
+    if ((e = cudaMemsetAsync(w.f2, 0, (16 + 8) * sizeof(double), st)) != cudaSuccess) return e;   // f2 + flags
+    if ((e = cudaMemcpyAsync(w.Qwork, w.Qb, (size_t)n * LB * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+    const dim3 gx((n + AT - 1) / AT, 1);
+    const int rowblocks = (n + 127) / 128;
+    int nl = 0;
+    for (int it = 0; it < NSI; ++it) {
+        atb_kernel<<<gx, 256, 0, st>>>(G, n, w.Qwork, n, n, n, LB, nullptr, w.X, n, 0, nullptr, w.flags, 0);        // X = G Q
+        atb_kernel<<<dim3(1, 1), 256, 0, st>>>(w.Qwork, n, w.X, n, n, LB, LB, nullptr, w.Hs, LB, 0, nullptr, w.flags, 0);  // H = Q'X
+        rr_small_eig_kernel<<<1, 16 * LB, 0, st>>>(w.Hs, w.theta, w.Rs, w.flags);
+        rr_rotate_kernel<<<rowblocks, 128, 0, st>>>(w.Qwork, w.X, w.Rs, n, w.Qr, w.Xr, w.flags);
+        rr_resid_kernel<<<LB, 256, 0, st>>>(w.Qr, w.Xr, w.theta, n, w.res, w.nx, w.flags);
+        rr_decide_kernel<<<1, 1024, 0, st>>>(w.Qr, w.Xr, w.theta, w.res, w.nx, n, tau2, min_wanted, tol_res,
+                                            it == NSI - 1 ? 1 : 0, w.Qwork, w.Qout, w.theta, w.flags);
+        for (int rep = 0; rep < 2; ++rep) {                                                    // CholeskyQR2
+            atb_kernel<<<dim3(1, 1), 256, 0, st>>>(w.Qwork, n, w.Qwork, n, n, LB, LB, nullptr, w.Ss, LB, 0, nullptr, w.flags, 0);
+            rr_chol32_kernel<<<1, LB, 0, st>>>(w.Ss, w.flags);
+            rr_trsm_kernel<<<rowblocks, 128, 0, st>>>(w.Qwork, w.Ss, n, w.flags);
+        }
+        nl += 12;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    deflate_kernel<<<(unsigned)(((int64_t)n * n + 255) / 256), 256, 0, st>>>(G, n, w.Qout, w.theta, w.flags, w.Ca, w.f2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const dim3 gs((n + AT - 1) / AT, (n + AT - 1) / AT);
+    double* cin = w.Ca;
+    double* cout = w.Cb;
+    for (int j = 0; j < NSQ; ++j) {
+        atb_kernel<<<gs, 256, 0, st>>>(cin, n, cin, n, n, n, n, w.f2 + j, cout, n, 1, w.f2 + j + 1, w.flags, 1,
+                                       w.f2, j, tau2, top1 ? w.theta : nullptr);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        double* tmp = cin; cin = cout; cout = tmp;
+    }
+    fast_finish_kernel<<<1, 256, 0, st>>>(n, NSQ, w.f2, tau2, top1, tau, nukeA, w.theta, w.Qout, w.Qb, Vs, lam, sigma, fvec,
+                                          svp, w.flags, LB);
+    if (launches) *launches += nl + 1 + NSQ + 1;
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 size_t eig_fast_work_doubles(int n) {
     // Qb, Qwork, Qout, X (n x 32 each) + theta (32) + Ca, Cb (n x n) + f2 (16) + flags (8 ints -> 8 doubles)
-    return (size_t)4 * n * SIB + SIB + (size_t)2 * n * n + 16 + 8 + 16;
+    // large n: + Qr, Xr (n x 32), Hs, Rs, Ss (32 x 32), res, nx (32)
+    return (size_t)6 * n * SIB + SIB + (size_t)2 * n * n + 16 + 8 + 16 + 3 * SIB * SIB + 2 * SIB;
 }
 
-bool eig_fast_supported(int n) { return n > 64 && n <= 512; }
-int eig_fast_max_block(int n) { return n <= 256 ? 32 : 16; }   // shared memory: block x 2 x n doubles must fit
+bool eig_fast_supported(int n) { return n > 64 && n <= kEigMaxN; }
+// small path: shared memory (block x 2 x n doubles) must fit; large path: always the 32-column block
+int eig_fast_max_block(int n) { return (n <= 256 || n > kEigSmallN) ? 32 : 16; }
 
 EigFastWork eig_fast_carve(double* base, int n) {
     EigFastWork w;
@@ -411,7 +662,14 @@ EigFastWork eig_fast_carve(double* base, int n) {
     w.Ca = base; base += (size_t)n * n;
     w.Cb = base; base += (size_t)n * n;
     w.f2 = base; base += 16;
-    w.flags = reinterpret_cast<int*>(base);
+    w.flags = reinterpret_cast<int*>(base); base += 8;
+    w.Qr = base; base += (size_t)n * SIB;
+    w.Xr = base; base += (size_t)n * SIB;
+    w.Hs = base; base += SIB * SIB;
+    w.Rs = base; base += SIB * SIB;
+    w.Ss = base; base += SIB * SIB;
+    w.res = base; base += SIB;
+    w.nx = base; base += SIB;
     return w;
 }
 
@@ -452,6 +710,8 @@ cudaError_t launch_init_block(double* Qb, int n, cudaStream_t st, int64_t* launc
 cudaError_t launch_eig_fast(const double* G, int n, double tau, int nukeA, EigFastWork w, double* lam, double* Vs,
                             double* sigma, double* fvec, int* svp, cudaStream_t st, int64_t* launches, int top1,
                             int bw, int max_steps) {
+    if (n > kEigSmallN)
+        return launch_eig_large(G, n, tau, nukeA, w, lam, Vs, sigma, fvec, svp, st, launches, top1, max_steps);
     if (bw != 16) bw = SIB;
     if (n > 256) bw = 16;
     // subspace-iteration steps attempted before falling back (launches after convergence exit at once, but each still

@@ -41,12 +41,14 @@ cudaError_t launch_gram_reduce(const double* partial, int nsplit, int nblk, int 
 
 // TMA-fed SYRK for a materialised dense X (syrk_tma.cu): 128 x 128 blocks, 16-row boxes, 4-stage mbarrier ring
 constexpr int kSyrkBlk = 128;
-constexpr int kEigMaxN = 512;
+constexpr int kEigMaxN = 2048;              // largest min(M, N): 16 x 16 blocks of 128 columns
+constexpr int kEigSmallN = 512;             // up to here: shared-memory / register-resident eigen kernels (eig.cu, eig_fast.cu)
+constexpr int kSyrkMaxBlk = 136;            // upper-triangular 128-blocks at N = 2048
 struct SyrkPlan {
     int nb, nblk, nsplit, ntiles, ncta;     // 128-blocks per dimension, upper-triangular blocks, -, 32-row tiles, CTAs
-    int nsplit_blk[10];                     // row splits (CTAs) of every block, proportional to its cost
-    int cta_begin[11];                      // first CTA of every block
-    int part_off[10];                       // first partial slot of every block
+    int nsplit_blk[kSyrkMaxBlk];            // row splits (CTAs) of every block, proportional to its cost
+    int cta_begin[kSyrkMaxBlk + 1];         // first CTA of every block
+    int part_off[kSyrkMaxBlk];              // first partial slot of every block
     size_t partial_bytes;
 };
 bool syrk_tma_eligible(const double* X, int64_t M, int64_t N, int64_t ld);
@@ -97,6 +99,8 @@ struct EigFastWork {
     double* Cb;      // n x n certificate pong
     double* f2;      // 16 squared Frobenius norms of the squaring chain
     int* flags;      // [0] converged [1] need_full [2] svp [3] SI steps [4] certified [5] sweeps of the last SI step
+    // large embeddings (n > kEigSmallN): rotated block, projected 32 x 32 problem, Gram of the basis, residuals / norms
+    double* Qr; double* Xr; double* Hs; double* Rs; double* Ss; double* res; double* nx;
 };
 size_t eig_fast_work_doubles(int n);
 bool eig_fast_supported(int n);
@@ -152,6 +156,10 @@ struct EpiArgs {
     // hankel=true (:214-216): the tile epilogue only writes the raw reconstruction A' = T diag(f) V_r' into An; the
     // anti-diagonal soft threshold, clamp, Z and Y follow in launch_hankel_finish
     int raw_only;
+    // streaming kernels, large N: column range [c0, c1) of one launch (c1 == 0: all columns) and an N x 32 scratch for
+    // the GEMM operand V_r diag(f) (set by the solver when N > kEigSmallN)
+    int c0, c1;
+    double* vf_work;
 };
 cudaError_t launch_epilogue(const EpiArgs& a, bool hankel, bool mode_u, int sm_count, cudaStream_t st,
                             int64_t* launches);

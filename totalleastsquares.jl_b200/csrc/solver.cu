@@ -301,7 +301,12 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     const size_t ws_bytes = (size_t)4 << 30;
     bool can_fused = !no_fact && !hk && fused_eligible(D, hankel, M, N);
     if (can_fused && !syrk_ok && (o.A || o.E || o.U || o.S || o.Vt)) can_fused = false;   // padded leading dimension: factored outputs only
-    const bool can_legacy = syrk_ok && !hk;
+    // large embeddings (n > 512): always the two-kernel pipeline on a materialised W (column-chunked streaming epilogue,
+    // T = W V_r by GEMM); the Gram takes the TMA SYRK when the shape allows it, else the generic DMMA kernel on W
+    const bool large_n = N > kEigSmallN;
+    if (large_n && hk)
+        return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: hankel=true is limited to min(M,N) <= %d", kEigSmallN);
+    const bool can_legacy = (syrk_ok || large_n) && !hk;
     const bool wants_fused = 4 * mn * 8 + mn * 2 + ws_bytes > free_b;      // Y x 2, W, Z (+ factors) do not fit
     const bool wants_inplace = 2 * mn * 8 + mn * 2 + ws_bytes > free_b;    // not even two copies of Y fit
     double votes[5] = {(double)M, can_legacy ? 1.0 : 0.0, can_fused ? 1.0 : 0.0, wants_fused ? 1.0 : 0.0,
@@ -324,7 +329,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     bool use_w = pc.use_w;
     // the one-pass kernel moves Y / T tiles with TMA (16-byte strides): an odd row count gets a padded leading dimension
     const int64_t ldp = fused ? M + (M & 1) : M;
-    bool fact = (use_w || fused) && !no_fact;
+    bool fact = (use_w || fused) && (!no_fact || large_n);
     DevBuf bMean;
     double* meanbuf = nullptr;
     if (hk) { CK(bMean.alloc((size_t)(M + N) * 8, st)); meanbuf = bMean.as<double>(); }
@@ -379,6 +384,21 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     if (!inplace_y) CK(bY1.alloc((size_t)ldp * N * 8, st));
     double* Ybuf[2] = {bY0.as<double>(), inplace_y ? bY0.as<double>() : bY1.as<double>()};
     CK(bPart.alloc(part_bytes, st));
+    // Gram of a materialised M x N matrix (W, Z): TMA-fed SYRK, or the generic DMMA kernel when the shape is not
+    // TMA-eligible (odd leading dimension, few rows)
+    auto gram_mat = [&](const double* X, double* Gdst) -> int {
+        if (syrk_ok) {
+            CK(launch_syrk_tma(X, M, N, M, splan, bPart.as<double>(), Gdst, st, L));
+        } else {
+            GramSrc g2;
+            g2.D = MatSrc{X, M}; g2.A = nullptr; g2.Y = nullptr; g2.A2 = nullptr; g2.ldw = M; g2.M = M; g2.N = N;
+            g2.im = 0.0; g2.eps = 0.0; g2.nonnegE = 0;
+            CK(launch_gram(g2, GRAM_D, false, plan, bPart.as<double>(), Gdst, st, L));
+        }
+        return TLSQ_OK;
+    };
+    DevBuf bVf;
+    if (large_n) CK(bVf.alloc((size_t)N * kStreamMaxRank * 8, st));
     CK(bG.alloc(((size_t)n * n + 8) * 8, st)); CK(bGn.alloc(((size_t)n * n + 8) * 8, st));
     CK(bG2.alloc(((size_t)n * n + 8) * 8, st));
     CK(bVs.alloc((size_t)n * n * 8, st)); CK(bVs2.alloc((size_t)n * n * 8, st));
@@ -419,7 +439,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     }
     bool have_q = false;
     bool last_was_fast = false;
-    int cur_bw = 16;
+    int cur_bw = large_n ? 32 : 16;     // large embeddings always iterate on the 32-column block (eig_fast.cu)
     int si_budget = 12;           // subspace steps launched per iteration: last iteration's count + margin
     // exact stop test: Z is materialised by the epilogue when the Frobenius bracket is expected to be undecided, its
     // Gram runs on the TMA SYRK kernel and lambda_max is bracketed by repeated squaring
@@ -457,7 +477,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
         // certificate that theta_1 is the largest eigenvalue; the full Jacobi is the fallback
         if (fast_ok) {
             CK(launch_init_block(fw.Qb, n, st, L));
-            CK(launch_eig_fast(Gb[0], n, 0.0, 1, fw, lam, Vs, sigma, fvec, dsvp, st, L, 1, 16));
+            CK(launch_eig_fast(Gb[0], n, 0.0, 1, fw, lam, Vs, sigma, fvec, dsvp, st, L, 1, cur_bw));
             CK(launch_eigh(Gb[0], n, nullptr, ew, lam, Vs, sms, st, L, fw.flags));
             CK(launch_copy_block(Vs, n, fw.Qb, fw.flags, st, L));
             have_q = true;
@@ -552,7 +572,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
             if (!gram_ready) {
                 {
                     Phase ph(h, TLSQ_PHASE_GRAM);
-                    if (use_w) CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), G, st, L));
+                    if (use_w) CKR(gram_mat(Wbuf, G));
                     else CK(launch_gram(gs, GRAM_W, hankel, plan, bPart.as<double>(), G, st, L));
                 }
                 CKR(allreduce(h, G, (size_t)n * n, kNcclSum));
@@ -657,6 +677,10 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 if (want_z && !Zbuf && !inplace_y) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
                 ea.Zout = (want_z && Zbuf) ? Zbuf : nullptr;
                 ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
+                ea.vf_work = bVf.as<double>();
+                if (large_n && svp_guess > kStreamMaxRank)
+                    return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: rank estimate %d > %d with min(M,N) = %lld > %d is outside "
+                                   "the accelerated path", svp_guess, kStreamMaxRank, (long long)N, kEigSmallN);
                 bool guarded = false;          // the launch below checks the rank guess on the device
                 int rp_launched = 0;
                 {
@@ -697,8 +721,6 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                     if (fast_ok) CK(cudaMemcpyAsync(hp + 4, fw.flags, 32, cudaMemcpyDeviceToHost, st));
                 }
                 if (fast_ok && was_fast_k) CK(cudaMemcpyAsync(hp + 8, fw.flags, 16, cudaMemcpyDeviceToHost, st));
-                const int nlead = n < 32 ? n : 32;
-                CK(cudaMemcpyAsync(hp + 16, lam, (size_t)nlead * 8, cudaMemcpyDeviceToHost, st));   // leading eigenvalues
                 // run-ahead: Gram + eigen step of iteration k+1 behind the epilogue, before the host looks at the result
                 const bool run_ahead = use_w && !no_ahead && !want_z && k < p.iters && attempt == 0;
                 const double t_enq = now_us();
@@ -707,7 +729,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                     CK(cudaEventRecord(h->ev_iter, st));
                     {
                         Phase ph(h, TLSQ_PHASE_GRAM);
-                        CK(launch_syrk_tma(Wbuf, M, N, M, splan, bPart.as<double>(), Gnext, st, L));
+                        CKR(gram_mat(Wbuf, Gnext));
                     }
                     CKR(allreduce(h, Gnext, (size_t)n * n, kNcclSum));
                     CKR(enqueue_eig(Gnext, 1.0 / mu_next));
@@ -745,16 +767,10 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 break;
             }
             if (fact) svpb[nxt] = svp;
-            // rank guess of the next iteration: the spectrum moves slowly, so count this iteration's leading (Ritz)
-            // values against the NEXT threshold 1/mu_{k+1} (30 % margin: a guess that is too large only costs a slightly
-            // slower specialisation, one that is too small a relaunch)
-            {
-                const double thr = 0.7 / mu_next;
-                int cnt = 0;
-                const int nlead = n < 32 ? n : 32;
-                for (int i = 0; i < nlead; ++i) cnt += (hp[16 + i] > 0.0 && sqrt(hp[16 + i]) >= thr) ? 1 : 0;
-                svp_pred = cnt > svp ? cnt : svp;
-            }
+            // (A rank guess from this iteration's leading Ritz values against the next threshold was tried: the bulk sits
+            // just below 1/mu_k and is above 1/mu_{k+1}, so it over-counts every iteration and costs a slower
+            // specialisation -- the last rank is the better guess; a jump costs one relaunch.)
+            svp_pred = svp;
         }
         if (fast_ok && was_fast_k) {
             int fl[4];
@@ -807,14 +823,14 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 CK(launch_alm_fused(f, hankel, Ybuf[cur], Tb[cur], Tb[nxt], G2, nullptr, sms, st, L));
                 CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             } else if (want_z && Zbuf) {
-                CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
+                CKR(gram_mat(Zbuf, G2));
                 CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             } else if (fact) {
                 // the bracket was not predicted: rebuild Z_k from the factored iterates, then the same SYRK
                 if (!Zbuf) { CK(bZ.alloc(mn * 8, st)); Zbuf = bZ.as<double>(); }
                 ea.Vs = Vb[nxt];               // V_k (Vs may already belong to the run-ahead eigen step)
                 CK(launch_z_from_factors(ea, hankel, svp, Zbuf, sms, st, L));
-                CK(launch_syrk_tma(Zbuf, M, N, M, splan, bPart.as<double>(), G2, st, L));
+                CKR(gram_mat(Zbuf, G2));
                 CKR(allreduce(h, G2, (size_t)n * n, kNcclSum));
             } else {
                 gs.A = Abuf[cur]; gs.Y = Ybuf[cur]; gs.A2 = Abuf[nxt]; gs.im = im; gs.eps = eps;

@@ -42,15 +42,18 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp_host, c
     // the guess the whole grid returns before touching anything and the host relaunches with the right RP.
     const int svp = svp_dev ? __ldg(svp_dev) : svp_host;
     if (svp > RP) return;
-    extern __shared__ double Vsm[];            // [N][RP]  (+ [N][RP] of V_{k-1} when FACT)
+    extern __shared__ double Vsm[];            // [NC][RP]  (+ [NC][RP] of V_{k-1} when FACT)
     __shared__ double fsm[RP > 0 ? RP : 1];
     const int N = (int)a.N;
-    double* Vpm = Vsm + (size_t)N * RP;
+    // column range of this launch: all N columns, or (PH == 2 only, large N: the V rows of all columns do not fit in
+    // shared memory) the chunk [c0, c1)
+    const int cb = a.c1 > 0 ? a.c0 : 0, ce = a.c1 > 0 ? a.c1 : N, NC = ce - cb;
+    double* Vpm = Vsm + (size_t)NC * RP;
     if (threadIdx.x < RP) fsm[threadIdx.x] = (int)threadIdx.x < svp ? __ldg(a.fvec + threadIdx.x) : 0.0;
-    for (int idx = threadIdx.x; idx < N * RP; idx += blockDim.x) {
-        const int j = idx % N, c = idx / N;
-        Vsm[j * RP + c] = c < svp ? __ldg(a.Vs + (int64_t)c * N + j) : 0.0;
-        if (FACT && PH != 1) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + j) : 0.0;
+    for (int idx = threadIdx.x; idx < NC * RP; idx += blockDim.x) {
+        const int j = idx % NC, c = idx / NC;
+        Vsm[j * RP + c] = c < svp ? __ldg(a.Vs + (int64_t)c * N + cb + j) : 0.0;
+        if (FACT && PH != 1) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + cb + j) : 0.0;
     }
     __syncthreads();
     double zz = 0.0;
@@ -113,19 +116,19 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp_host, c
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             dv[u] = av[u] = yv[u] = 0.0;
-            if (u < N) {
-                const int64_t off = (int64_t)u * a.ldw + row;
-                dv[u] = src_at<HANKEL>(a.D, row, u);
+            if (cb + u < ce) {
+                const int64_t off = (int64_t)(cb + u) * a.ldw + row;
+                dv[u] = src_at<HANKEL>(a.D, row, cb + u);
                 if (!FACT) av[u] = __ldg(a.Ap + off);
                 yv[u] = __ldg(a.Yp + off);
             }
         }
-        for (int j0 = 0; j0 < N; j0 += UB) {
+        for (int j0 = cb; j0 < ce; j0 += UB) {
 #pragma unroll
             for (int u = 0; u < UB; ++u) {
                 const int j = j0 + UB + u;
                 dn[u] = an_[u] = yn_[u] = 0.0;
-                if (j < N) {
+                if (j < ce) {
                     const int64_t off = (int64_t)j * a.ldw + row;
                     dn[u] = src_at<HANKEL>(a.D, row, j);
                     if (!FACT) an_[u] = __ldg(a.Ap + off);
@@ -135,14 +138,14 @@ alm_stream_kernel(const EpiArgs a, const double* __restrict__ W, int svp_host, c
 #pragma unroll
             for (int u = 0; u < UB; ++u) {
                 const int j = j0 + u;
-                if (j < N) {
+                if (j < ce) {
                     const int64_t off = (int64_t)j * a.ldw + row;
                     const double d = dv[u], yp = yv[u];
                     double an = 0.0, ap = 0.0;
-                    if (RP > 0) an = dot_rp<RP>(tr, Vsm + j * RP);
+                    if (RP > 0) an = dot_rp<RP>(tr, Vsm + (j - cb) * RP);
                     if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;   // A .= max.(A, 0)   :218
                     if (FACT) {                                                       // A_{k-1} from its factors
-                        if (RP > 0) ap = dot_rp<RP>(tp, Vpm + j * RP);
+                        if (RP > 0) ap = dot_rp<RP>(tp, Vpm + (j - cb) * RP);
                         if (a.nonnegA) ap = (__double_as_longlong(ap) > 0) ? ap : 0.0;
                     } else {
                         ap = av[u];
@@ -179,11 +182,12 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
                   double* __restrict__ out) {
     extern __shared__ double Vsm[];
     const int N = (int)a.N;
-    double* Vpm = Vsm + (size_t)N * RP;
-    for (int idx = threadIdx.x; idx < N * RP; idx += blockDim.x) {
-        const int j = idx % N, c = idx / N;
-        Vsm[j * RP + c] = c < svp ? __ldg(V + (int64_t)c * N + j) : 0.0;
-        if (ZMODE) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + j) : 0.0;
+    const int cb = a.c1 > 0 ? a.c0 : 0, ce = a.c1 > 0 ? a.c1 : N, NC = ce - cb;      // column chunk of this launch
+    double* Vpm = Vsm + (size_t)NC * RP;
+    for (int idx = threadIdx.x; idx < NC * RP; idx += blockDim.x) {
+        const int j = idx % NC, c = idx / NC;
+        Vsm[j * RP + c] = c < svp ? __ldg(V + (int64_t)c * N + cb + j) : 0.0;
+        if (ZMODE) Vpm[j * RP + c] = c < a.svp_prev ? __ldg(a.Vp + (int64_t)c * N + cb + j) : 0.0;
     }
     __syncthreads();
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < a.M;
@@ -194,16 +198,16 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
             tr[c] = c < svp ? __ldg(T + (int64_t)c * a.M + row) : 0.0;
             if (ZMODE) tp[c] = c < a.svp_prev ? __ldg(a.Tp + (int64_t)c * a.M + row) : 0.0;
         }
-        for (int j = 0; j < N; ++j) {
+        for (int j = cb; j < ce; ++j) {
             const int64_t off = (int64_t)j * a.ldw + row;
             double an = 0.0;
-            const double* v = Vsm + j * RP;
+            const double* v = Vsm + (j - cb) * RP;
 #pragma unroll
             for (int c = 0; c < RP; ++c) an = fma(tr[c], v[c], an);
             if (a.nonnegA) an = (__double_as_longlong(an) > 0) ? an : 0.0;
             if (ZMODE == 0) { out[off] = an; continue; }
             double ap = 0.0;
-            const double* vp = Vpm + j * RP;
+            const double* vp = Vpm + (j - cb) * RP;
 #pragma unroll
             for (int c = 0; c < RP; ++c) ap = fma(tp[c], vp[c], ap);
             if (a.nonnegA) ap = (__double_as_longlong(ap) > 0) ? ap : 0.0;
@@ -224,6 +228,24 @@ fact_dense_kernel(const EpiArgs a, const double* __restrict__ T, const double* _
 // padded rank of the specialised kernels: 0, 4, 8, 12, 16, 24, 32
 inline int rp_of(int svp) { return svp <= 16 ? ((svp + 3) & ~3) : ((svp + 7) & ~7); }
 
+// columns per launch so that `copies` blocks of [NC][RP] doubles fit in shared memory (all N when they do)
+inline int chunk_cols(int64_t N, int rp, int copies) {
+    if (rp == 0) return (int)N;
+    const int64_t fit = ((int64_t)200 * 1024 / ((int64_t)rp * 8 * copies)) & ~(int64_t)7;
+    return (int)(N <= fit ? N : fit);
+}
+
+// B (N x RP) = V_r diag(f): the right factor of T = (W V_r) .* f as a GEMM operand (rank read from the device)
+__global__ void __launch_bounds__(256)
+build_vf_kernel(const double* __restrict__ Vs, const double* __restrict__ fvec, const int* __restrict__ svp_dev,
+                int svp_host, int N, int RP, double* __restrict__ B) {
+    const int svp = svp_dev ? __ldg(svp_dev) : svp_host;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * RP; idx += gridDim.x * blockDim.x) {
+        const int c = idx / N;
+        B[idx] = (c < svp && svp <= RP) ? __ldg(Vs + idx) * __ldg(fvec + c) : 0.0;
+    }
+}
+
 template <int RP>
 cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, const int* svp_dev, bool hankel, int sm_count,
                              cudaStream_t st) {
@@ -242,6 +264,30 @@ cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, const i
         if (smem_ > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
         if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem_, st>>>(a, W, svp, svp_dev);                     \
     } while (0)
+    const int nc = chunk_cols(a.N, RP, fact ? 2 : 1);
+    if (nc < a.N) {
+        // large N: T = W (V_r diag(f)) as a DMMA GEMM (a.vf_work: N x 32 scratch), then the element-wise pass per
+        // column chunk with the chunk's rows of V_{k-1}, V_k in shared memory
+        if (!fact || !a.vf_work) return cudaErrorInvalidValue;
+        build_vf_kernel<<<64, 256, 0, st>>>(a.Vs, a.fvec, svp_dev, svp, (int)a.N, RP, a.vf_work);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = launch_gemm_any(W, a.M, (int)a.N, a.ldw, a.vf_work, RP, a.Tn, st, nullptr)) != cudaSuccess) return e;
+        for (int c0 = 0; c0 < a.N && e == cudaSuccess; c0 += nc) {
+            EpiArgs ac = a;
+            ac.c0 = c0;
+            ac.c1 = (int)(c0 + nc < a.N ? c0 + nc : a.N);
+            const size_t smc = (size_t)2 * (ac.c1 - ac.c0) * RP * sizeof(double);
+            auto kern_h = alm_stream_kernel<RP, true, true, 2>;
+            auto kern_d = alm_stream_kernel<RP, false, true, 2>;
+            if (smc > 32 * 1024)
+                e = cudaFuncSetAttribute(hankel ? kern_h : kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc);
+            if (e != cudaSuccess) break;
+            if (hankel) kern_h<<<(unsigned)blocks, 128, smc, st>>>(ac, W, svp, svp_dev);
+            else kern_d<<<(unsigned)blocks, 128, smc, st>>>(ac, W, svp, svp_dev);
+        }
+        if (e != cudaSuccess) return e;
+        return cudaGetLastError();
+    }
     const size_t sm1 = (size_t)a.N * RP * sizeof(double);
     if (split) {
         if (hankel) { TLSQ_STREAM_LAUNCH(true, true, 1, sm1); if (e == cudaSuccess) TLSQ_STREAM_LAUNCH(true, true, 2, 2 * sm1); }
@@ -259,20 +305,25 @@ cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, const i
 template <int RP, int ZMODE>
 cudaError_t launch_fact_rp(const EpiArgs& a, const double* T, const double* V, int svp, bool hankel, double* out,
                            int sm_count, cudaStream_t st) {
-    const size_t smem = (size_t)a.N * RP * sizeof(double) * (ZMODE ? 2 : 1);
     int64_t blocks = (a.M + 127) / 128;
     int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     cudaError_t e = cudaSuccess;
-    if (hankel) {
-        auto kern = fact_dense_kernel<RP, true, ZMODE>;
-        if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(a, T, V, svp, out);
-    } else {
-        auto kern = fact_dense_kernel<RP, false, ZMODE>;
-        if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(a, T, V, svp, out);
+    const int nc = chunk_cols(a.N, RP, ZMODE ? 2 : 1);           // all N columns unless V does not fit in shared memory
+    for (int c0 = 0; c0 < a.N && e == cudaSuccess; c0 += nc) {
+        EpiArgs ac = a;
+        if (nc < a.N) { ac.c0 = c0; ac.c1 = (int)(c0 + nc < a.N ? c0 + nc : a.N); }
+        const size_t smem = (size_t)(nc < a.N ? ac.c1 - ac.c0 : a.N) * RP * sizeof(double) * (ZMODE ? 2 : 1);
+        if (hankel) {
+            auto kern = fact_dense_kernel<RP, true, ZMODE>;
+            if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(ac, T, V, svp, out);
+        } else {
+            auto kern = fact_dense_kernel<RP, false, ZMODE>;
+            if (smem > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem, st>>>(ac, T, V, svp, out);
+        }
     }
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
@@ -281,9 +332,8 @@ cudaError_t launch_fact_rp(const EpiArgs& a, const double* T, const double* V, i
 }  // namespace
 
 bool stream_factored_fits(int64_t N, int svp, int svp_prev) {
-    if (svp > kStreamMaxRank || svp_prev > kStreamMaxRank) return false;
-    const int rp = rp_of(svp > svp_prev ? svp : svp_prev);
-    return (size_t)N * rp * 8 * 2 <= (size_t)200 * 1024;
+    (void)N;        // any N: when the V blocks do not fit in shared memory the element-wise pass runs per column chunk
+    return svp <= kStreamMaxRank && svp_prev <= kStreamMaxRank;
 }
 
 int stream_rank_pad(int svp, int svp_prev, bool fact) { return rp_of(fact && svp_prev > svp ? svp_prev : svp); }
