@@ -173,6 +173,10 @@ constexpr int kStreamMaxRank = 32;
 cudaError_t launch_stream_epilogue(const EpiArgs& a, const double* W, int svp, bool hankel, int sm_count,
                                    cudaStream_t st, int64_t* launches, bool svp_on_device = false);
 int stream_rank_pad(int svp, int svp_prev, bool fact);
+// TMA-staged form of the same two kernels (stream_tma.cu): 128-row x 8-column boxes through a 4-stage mbarrier ring
+bool stream_tma_eligible(const EpiArgs& a, const double* W, int rp, bool hankel);
+cudaError_t launch_stream_tma(const EpiArgs& a, const double* W, int rp, int svp, const int* svp_dev, bool hankel,
+                              int sm_count, cudaStream_t st);
 // can the factored form be used for this (N, svp, svp_prev)?  (two N x RP blocks of V must fit in shared memory)
 bool stream_factored_fits(int64_t N, int svp, int svp_prev);
 // dense helpers for the factored iterate:  A = clamp(T V')   and   Z = (D - A_k) - E_k  with A_{k-1}, A_k factored

@@ -522,9 +522,9 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     //    from device memory; a guess that turns out too small makes the kernels return untouched and is relaunched;
     //  * while the host waits for ||Z||_F^2 of iteration k, the Gram and the eigen step of iteration k+1 are already
     //    enqueued ("run-ahead"; skipped when iteration k may converge, so at most nothing is wasted in practice).
-    static const bool no_ahead = getenv("TLSQ_NO_RUNAHEAD") != nullptr;
-    static const bool no_spec = getenv("TLSQ_NO_SPECULATE") != nullptr;
-    static const bool trace = getenv("TLSQ_TRACE") != nullptr;
+    const bool no_ahead = getenv("TLSQ_NO_RUNAHEAD") != nullptr;
+    const bool no_spec = getenv("TLSQ_NO_SPECULATE") != nullptr;
+    const bool trace = getenv("TLSQ_TRACE") != nullptr;
     auto now_us = []() {
         struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
         return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
@@ -609,7 +609,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 const double ratio = fmin(prev_fro / prev_prev_fro, 1.0);
                 want_z = prev_fro * ratio < 4.0 * sqrt(dmin) * p.tol;
             }
-            static const bool no_pred = getenv("TLSQ_NO_PREDICT_Z") != nullptr;     // test hook: exercise the retry below
+            const bool no_pred = getenv("TLSQ_NO_PREDICT_Z") != nullptr;     // test hook: exercise the retry below
             if (inplace_y && no_pred && !exact_cost) want_z = false;
             if (inplace_y && k >= two_phase_from) want_z = true;
         }
@@ -945,7 +945,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
         //   C'C = R'R                     Gram formed FROM THE DATA in the rotated, scaled basis + Cholesky
         //   K = R diag(s~) = U_K S V_K'   one-sided Jacobi of the n x n factor: K'K = V' W'W V exactly (to eps kappa(C)^2)
         //   W = (W V V_K S^-1) S (V V_K)' singular values to eps*s_1 like LAPACK's, V = V V_K, U = W V S^-1
-        static const bool no_refine = getenv("TLSQ_NO_SVD_REFINE") != nullptr;
+        const bool no_refine = getenv("TLSQ_NO_SVD_REFINE") != nullptr;
         double* Vfin = Vs;
         if (!no_refine) {
             double* Cbuf = o.U;

@@ -264,6 +264,10 @@ cudaError_t launch_stream_rp(const EpiArgs& a, const double* W, int svp, const i
         if (smem_ > 32 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_); \
         if (e == cudaSuccess) kern<<<(unsigned)blocks, 128, smem_, st>>>(a, W, svp, svp_dev);                     \
     } while (0)
+    // TMA-staged kernels (stream_tma.cu) whenever the shape allows them; the register-prefetch kernels below remain for
+    // small / oddly aligned problems, the dense iterate and the column-chunked large-N form
+    if (fact && RP >= 4 && stream_tma_eligible(a, W, RP, hankel))
+        return launch_stream_tma(a, W, RP, svp, svp_dev, hankel, sm_count, st);
     const int nc = chunk_cols(a.N, RP, fact ? 2 : 1);
     if (nc < a.N) {
         // large N: T = W (V_r diag(f)) as a DMMA GEMM (a.vf_work: N x 32 scratch), then the element-wise pass per

@@ -104,7 +104,8 @@ __device__ __forceinline__ void diag_stage(double (&acc)[4][8][2], const uint8_t
 }
 
 __global__ void __launch_bounds__(256, 1)
-syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ partial, const SyrkPlan plan) {
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ partial,
+                const __grid_constant__ SyrkPlan plan) {
     // 1024-byte alignment is required by the 128B swizzle pattern.  The pointer is NOT re-aligned with integer
     // arithmetic: that would turn every fragment load into a generic LD instead of LDS.
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -241,7 +242,8 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, double* __restrict__ p
 }
 
 // G[i,j] = G[j,i] = sum over the splits of block(i,j), fixed order; diagonal blocks only hold their upper 32-tiles
-__global__ void syrk_reduce_kernel(const double* __restrict__ partial, const SyrkPlan plan, int N, double* __restrict__ G) {
+__global__ void syrk_reduce_kernel(const double* __restrict__ partial, const __grid_constant__ SyrkPlan plan, int N,
+                                   double* __restrict__ G) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * N) return;
     int i = (int)(idx % N), j = (int)(idx / N);
