@@ -112,6 +112,26 @@ int tlsq_rpca_f64_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N,
                       double* A, double* E, double* U, double* S, double* Vt,
                       int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist);
 
+/* ---- rpca with the reference's plugin callables `svd` / `opnorm` (src/robustPCA.jl:168-169; used at :177, :193-197,
+ * :225; reference test test/runtests.jl:384-398).  A Julia closure reaches the library as a C function pointer
+ * (@cfunction) plus an opaque `user` pointer.  The matrices cross the boundary in HOST memory (column-major), so every
+ * call costs a device->host and a host->device copy: this is the reference's plugin hook, not the fast path.  NULL
+ * selects the built-in device implementation.  Single GPU, host pointers, any orientation, min(M,N) <= 2048.
+ *  svd_fn   : thin or truncated SVD of Z (M x N): fill U (M x r, column-major), S (r, descending), Vt (r x N, leading
+ *             dimension r) with 0 <= r <= min(M,N) and return r (< 0: error).  Called for k >= 2 with the current `sv`
+ *             like the reference's svd(Z, sv) (:196); the first iteration always uses the built-in SVD (:193-194).
+ *  opnorm_fn: returns (an estimate of) ||Z||_2 (:177, :225).
+ * Outputs as tlsq_rpca_f64; when the last SVD came from svd_fn with r < d the remaining columns / entries of U, S, Vt
+ * are zero. */
+typedef int64_t (*tlsq_svd_fn)(void* user, const double* Z, int64_t M, int64_t N, int64_t sv,
+                               double* U, double* S, double* Vt);
+typedef double  (*tlsq_opnorm_fn)(void* user, const double* Z, int64_t M, int64_t N);
+int tlsq_rpca_cb_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N,
+                     double lambda, int64_t maxrank, int64_t iters, double tol, double rho, uint32_t flags,
+                     tlsq_svd_fn svd_fn, tlsq_opnorm_fn opnorm_fn, void* user,
+                     double* A, double* E, double* U, double* S, double* Vt,
+                     int64_t* sv, int64_t* iters_done, int32_t* converged, double* hist);
+
 /* ---- lowrankfilter : replaces lowrankfilter(y, n; lag=1, sv=0, tol=1e-3, kwargs...) src/robustPCA.jl:119-128
  * for a single channel.  The K x n Hankel embedding (K = (Ns-n)/lag+1, :81) is indexed implicitly from y and is
  * never materialised; the result is the anti-diagonal average of the low-rank part (:127 -> :28-39, :53-68).

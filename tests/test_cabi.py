@@ -57,12 +57,22 @@ def test_host_argument_validation():
         T.lowrankfilter(y, 4, lag=5)
     with pytest.raises(AssertionError):
         T.hankel(y, 60)
-    with pytest.raises(TypeError):                # Float64 only, no fallback
-        T.rpca(np.zeros((4, 4), dtype=np.float32))
-    with pytest.raises(NotImplementedError):      # custom svd cannot cross the C ABI
-        T.rpca(np.zeros((4, 4)), svd=lambda Z, k: None)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):                # complex element types are not accelerated; no fallback
+        T.rpca(np.zeros((4, 4), dtype=np.complex128))
+    with pytest.raises(NotImplementedError):      # arbitrary mu callables cannot cross the C ABI (two built-ins can)
         T.rpca_ga(np.zeros((4, 4)), 2, mu=lambda s, w, U: s)
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful without a GPU")
+def test_float32_and_callables_still_need_the_gpu():
+    """Float32 inputs are promoted and svd / opnorm callables cross the C ABI as function pointers -- both still end
+    in the CUDA library (no CPU fallback)."""
+    with pytest.raises(T.TlsqError) as ei:
+        T.rpca(np.ones((6, 4), dtype=np.float32))
+    assert ei.value.code == T._cabi.TLSQ_ERR_NO_DEVICE
+    with pytest.raises(T.TlsqError) as ei:
+        T.rpca(np.ones((6, 4)), svd=lambda Z, k: np.linalg.svd(Z, full_matrices=False), opnorm=lambda Z: 1.0)
+    assert ei.value.code == T._cabi.TLSQ_ERR_NO_DEVICE
 
 
 def test_shard_rows_partition():

@@ -209,8 +209,18 @@ def rpca(D, *, lam: Optional[float] = None, maxrank: Optional[int] = None, iters
     lam = kwargs.pop("λ", lam)
     rho = kwargs.pop("ρ", rho)
     if svd is not None or opnorm is not None:
-        raise NotImplementedError("rpca: custom svd/opnorm callables are outside the accelerated path "
-                                  "(no CPU fallback); use the defaults")
+        # the reference's plugin hooks (:168-169): the callables run on the host, the rest of the iteration on the GPU
+        return _rpca_callables(D, svd, opnorm, lam=lam, maxrank=maxrank, iters=iters, tol=tol, rho=rho, verbose=verbose,
+                               nonnegA=nonnegA, nonnegE=nonnegE, hankel=hankel, nukeA=nukeA, return_info=return_info,
+                               want_svd=want_svd)
+    f32 = _as_float32_request(D)
+    if f32 is not None:
+        # Float32 inputs (reference: rpca(D::Matrix{Float32})): computed in Float64 on the GPU, returned as Float32
+        res = rpca(f32, lam=lam, maxrank=maxrank, iters=iters, tol=tol if tol is not None else
+                   math.sqrt(float(np.finfo(np.float32).eps)), rho=rho, verbose=verbose, nonnegA=nonnegA, nonnegE=nonnegE,
+                   hankel=hankel, nukeA=nukeA, return_info=return_info, want_svd=want_svd, want_E=want_E,
+                   exact_cost=exact_cost)
+        return _cast_result_float32(res)
     lib = load()
     Da = _Arr(D, "D")
     if len(Da.shape) != 2:
@@ -275,6 +285,99 @@ def rpca(D, *, lam: Optional[float] = None, maxrank: Optional[int] = None, iters
     return A, E, s, int(sv.value)
 
 
+
+# ------------------------------------------------------------------------------------------------------
+# Float32 promotion and the plugin callables of rpca
+# ------------------------------------------------------------------------------------------------------
+def _as_float32_request(x):
+    """Float64 copy of a Float32 NumPy array / CUDA tensor (None for anything else)."""
+    if _is_torch(x):
+        import torch
+        return x.double() if x.dtype == torch.float32 else None
+    a = np.asarray(x)
+    return np.asfortranarray(a.astype(np.float64)) if a.dtype == np.float32 else None
+
+
+def _cast_result_float32(res):
+    def cast(v):
+        if v is None or isinstance(v, (int, dict)):
+            return v
+        if isinstance(v, SVD):
+            return SVD(cast(v.U), cast(v.S), cast(v.Vt))
+        return v.float() if _is_torch(v) else np.asarray(v, dtype=np.float32, order="F")
+    return tuple(cast(v) for v in res) if isinstance(res, tuple) else cast(res)
+
+
+def _rpca_callables(D, svd, opnorm, *, lam, maxrank, iters, tol, rho, verbose, nonnegA, nonnegE, hankel, nukeA,
+                    return_info, want_svd):
+    """rpca(D; svd=f, opnorm=g): `f(Z, sv)` returns an object with fields U, S, Vt (or a (U, S, Vt) tuple) -- possibly
+    truncated --, `g(Z)` a real number (src/robustPCA.jl:168-169, 177, 193-197, 225; test/runtests.jl:384-398)."""
+    lib = load()
+    Dn = np.asfortranarray(np.asarray(D.detach().cpu().numpy() if _is_torch(D) else D, dtype=np.float64))
+    if Dn.ndim != 2:
+        raise TypeError("rpca: D must be a matrix")
+    M, N = Dn.shape
+    d = min(M, N)
+    if lam is None:
+        lam = 1.0 / math.sqrt(max(M, N))
+    if tol is None:
+        tol = math.sqrt(np.finfo(np.float64).eps)
+    errors = []
+
+    def svd_tramp(_user, Zp, m, n, sv, Up, Sp, Vtp):
+        try:
+            Z = np.ctypeslib.as_array(Zp, shape=(n, m)).T                      # column-major M x N view
+            res = svd(Z, int(sv))
+            U, S, Vt = (res.U, res.S, res.Vt) if hasattr(res, "Vt") else res
+            U, S, Vt = np.asarray(U, dtype=np.float64), np.asarray(S, dtype=np.float64), np.asarray(Vt, dtype=np.float64)
+            r = int(min(S.shape[0], min(m, n)))
+            np.ctypeslib.as_array(Up, shape=(r, m))[:] = U[:, :r].T             # M x r, column-major
+            np.ctypeslib.as_array(Sp, shape=(r,))[:] = S[:r]
+            np.ctypeslib.as_array(Vtp, shape=(n, r))[:] = Vt[:r, :].T           # r x N, leading dimension r
+            return r
+        except Exception as exc:                                                # noqa: BLE001 - re-raised after the C call
+            errors.append(exc)
+            return -1
+
+    def opn_tramp(_user, Zp, m, n):
+        try:
+            return float(opnorm(np.ctypeslib.as_array(Zp, shape=(n, m)).T))
+        except Exception as exc:                                                # noqa: BLE001
+            errors.append(exc)
+            return float("nan")
+
+    svd_c = _cabi.SVD_FN(svd_tramp) if svd is not None else C.cast(None, _cabi.SVD_FN)
+    opn_c = _cabi.OPNORM_FN(opn_tramp) if opnorm is not None else C.cast(None, _cabi.OPNORM_FN)
+    flags = (_cabi.TLSQ_NONNEG_A if nonnegA else 0) | (_cabi.TLSQ_NONNEG_E if nonnegE else 0) | \
+            (_cabi.TLSQ_HANKEL if hankel else 0) | (0 if nukeA else _cabi.TLSQ_NO_NUKE_A)
+    A = np.empty((M, N), order="F"); E = np.empty((M, N), order="F")
+    U = np.empty((M, d), order="F") if want_svd else None
+    S = np.empty((d,)) if want_svd else None
+    Vt = np.empty((d, N), order="F") if want_svd else None
+    p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None          # noqa: E731
+    sv, its, conv = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    hist = np.zeros((max(int(iters), 1), 3))
+    h = get_handle(None)
+    _cabi.check(lib.tlsq_use_own_stream(h))
+    code = lib.tlsq_rpca_cb_f64(h, p(Dn), M, N, float(lam), int(maxrank) if maxrank is not None else 0, int(iters),
+                                float(tol), float(rho), flags, svd_c, opn_c, None, p(A), p(E), p(U), p(S), p(Vt),
+                                C.byref(sv), C.byref(its), C.byref(conv), C.c_void_p(hist.ctypes.data))
+    if errors:
+        raise errors[0]
+    _cabi.check(code)
+    k = int(its.value)
+    if verbose:
+        for row in hist[:k]:
+            print(f"{int(row[0])} cost: {abs(row[2]):.4g}")
+        if conv.value:
+            print("converged")
+    if not conv.value:
+        warnings.warn(f"Maximum number of iterations reached, cost: {abs(hist[k - 1, 2]) if k else float('nan')}, tol: {tol}")
+    s = SVD(U, S, Vt) if want_svd else None
+    if return_info:
+        return A, E, s, int(sv.value), {"iters": k, "converged": bool(conv.value), "hist": hist[:k]}
+    return A, E, s, int(sv.value)
+
 # ------------------------------------------------------------------------------------------------------
 # lowrankfilter / hankel / unhankel
 # ------------------------------------------------------------------------------------------------------
@@ -287,7 +390,21 @@ def lowrankfilter(y, n: Optional[int] = None, *, sv: int = 0, lag: int = 1, tol:
     lam = kwargs.pop("λ", lam)
     rho = kwargs.pop("ρ", rho)
     if svd is not None or opnorm is not None:
-        raise NotImplementedError("lowrankfilter: custom svd/opnorm callables are outside the accelerated path")
+        # plugin callables (test/runtests.jl:384-398): the reference's own composition (:120-127) with rpca on the
+        # materialised trajectory matrix -- the callables need the whole matrix on the host anyway
+        yn = np.asarray(y.detach().cpu().numpy() if _is_torch(y) else y, dtype=np.float64)
+        Ns0 = yn.shape[0]
+        Dch0 = 1 if yn.ndim == 1 else yn.shape[1]
+        n0 = min(Ns0 // 20, 2000) if n is None else n
+        A = rpca(globals()["hankel"](yn, n0, lag), lam=lam, maxrank=maxrank, iters=iters, tol=tol, rho=rho,
+                 verbose=verbose, nonnegA=nonnegA, nonnegE=nonnegE, hankel=hankel, nukeA=nukeA, svd=svd, opnorm=opnorm,
+                 want_svd=False)[0]
+        return unhankel(A, lag, Ns0, Dch0)
+    f32 = _as_float32_request(y)
+    if f32 is not None:
+        return _cast_result_float32(lowrankfilter(f32, n, sv=sv, lag=lag, tol=tol, lam=lam, maxrank=maxrank, iters=iters,
+                                                  rho=rho, verbose=verbose, nonnegA=nonnegA, nonnegE=nonnegE,
+                                                  hankel=hankel, nukeA=nukeA, return_info=return_info))
     ya = _Arr(y, "y")
     Dch = 1 if len(ya.shape) == 1 else int(ya.shape[1])
     Ns = ya.shape[0]
@@ -411,6 +528,11 @@ def rpca_ga(X, r: Optional[int] = None, U=None, *, verbose: bool = False, tol: f
         else:
             raise NotImplementedError("rpca_ga: only mu!, entrywise_trimmed_mean and entrywise_median are accelerated; "
                                       "arbitrary callables cannot cross the C ABI (no CPU fallback)")
+    f32 = _as_float32_request(X)
+    if f32 is not None:
+        q0d = None if q0 is None else (_as_float32_request(q0) if _as_float32_request(q0) is not None else q0)
+        return _cast_result_float32(rpca_ga(f32, r, U, verbose=verbose, tol=tol, iters=iters, mu=mu, q0=q0d,
+                                            return_info=return_info))
     Xa = _Arr(X, "X")
     if len(Xa.shape) != 2:
         raise TypeError("rpca_ga: X must be a matrix")

@@ -24,6 +24,11 @@ _LRF_MC_ARGS = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C
                 C.c_double, C.c_double, C.c_uint32, vp, c_i64p, c_i64p, c_i32p, vp]
 _GA_ARGS = [vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_double, C.c_int64, vp, c_i64p]
 
+# plugin callables (tlsq_svd_fn / tlsq_opnorm_fn of include/tlsq_b200.h)
+SVD_FN = C.CFUNCTYPE(C.c_int64, vp, c_dp, C.c_int64, C.c_int64, C.c_int64, c_dp, c_dp, c_dp)
+OPNORM_FN = C.CFUNCTYPE(C.c_double, vp, c_dp, C.c_int64, C.c_int64)
+_RPCA_CB_ARGS = _RPCA_ARGS[:10] + [SVD_FN, OPNORM_FN, vp] + _RPCA_ARGS[10:]
+
 SIGNATURES = {
     "tlsq_abi_version": (C.c_int, []),
     "tlsq_last_error": (C.c_char_p, []),
@@ -39,6 +44,7 @@ SIGNATURES = {
     "tlsq_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "tlsq_rpca_f64": (C.c_int, _RPCA_ARGS),
     "tlsq_rpca_f64_dev": (C.c_int, _RPCA_ARGS),
+    "tlsq_rpca_cb_f64": (C.c_int, _RPCA_CB_ARGS),
     "tlsq_lowrankfilter_f64": (C.c_int, _LRF_ARGS),
     "tlsq_lowrankfilter_f64_dev": (C.c_int, _LRF_ARGS),
     "tlsq_rpca_ga_f64": (C.c_int, _GA_ARGS),

@@ -618,6 +618,13 @@ __global__ void scale_cols_floor_kernel(const double* __restrict__ V, const doub
     if (threadIdx.x == 0) st_out[c] = s;
     for (int i = threadIdx.x; i < n; i += blockDim.x) B[(int64_t)c * n + i] = V[(int64_t)c * n + i] * f;
 }
+// B[:, c] = V[:, c] * f[c] for the first `cols` columns (n rows)
+__global__ void scale_cols_mulvec_kernel(const double* __restrict__ V, const double* __restrict__ f, int n,
+                                         double* __restrict__ B) {
+    const int c = blockIdx.x;
+    const double s = f[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) B[(int64_t)c * n + i] = V[(int64_t)c * n + i] * s;
+}
 // K[:, c] = R[:, c] * st[c]
 __global__ void scale_cols_mul_kernel(const double* __restrict__ R, const double* __restrict__ st, int n,
                                       double* __restrict__ K) {
@@ -735,6 +742,14 @@ cudaError_t launch_scale_cols_floor(const double* V, const double* sigma, int n,
 cudaError_t launch_scale_cols_mul(const double* R, const double* sc, int n, double* K, cudaStream_t st,
                                   int64_t* launches) {
     scale_cols_mul_kernel<<<n, 128, 0, st>>>(R, sc, n, K);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_cols_mulvec(const double* V, const double* f, int n, int cols, double* B, cudaStream_t st,
+                                     int64_t* launches) {
+    if (cols < 1) return cudaSuccess;
+    scale_cols_mulvec_kernel<<<cols, 128, 0, st>>>(V, f, n, B);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

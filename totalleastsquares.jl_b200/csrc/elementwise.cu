@@ -322,6 +322,26 @@ hankel_finish_kernel(const EpiArgs a, const double* __restrict__ mean) {
     if ((threadIdx.x & 31) == 0) atomicAdd(a.zz, zz);
 }
 
+// dense iterate, plain element-wise tail of an ALM iteration (callback path, solver.cu):
+//   A = max(A, 0) [nonnegA] ; Z = (D - A) - E ; Y += mu Z ; zz += ||Z||_F^2              src/robustPCA.jl:217-222
+__global__ void __launch_bounds__(256)
+dense_update_kernel(const double* __restrict__ D, double* __restrict__ A, const double* __restrict__ E,
+                    double* __restrict__ Y, double* __restrict__ Z, int64_t total, double mu, int nonnegA,
+                    double* __restrict__ zz_out) {
+    double zz = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        double an = A[idx];
+        if (nonnegA) { an = (__double_as_longlong(an) > 0) ? an : 0.0; A[idx] = an; }
+        const double z = __dsub_rn(__dsub_rn(D[idx], an), E[idx]);
+        Y[idx] = __dadd_rn(Y[idx], __dmul_rn(mu, z));
+        Z[idx] = z;
+        zz = fma(z, z, zz);
+    }
+    zz = warp_sum(zz);
+    if ((threadIdx.x & 31) == 0) atomicAdd(zz_out, zz);
+}
+
 __global__ void __launch_bounds__(256)
 soft_hankel_apply_kernel(double* __restrict__ X, int64_t M, int64_t N, const double* __restrict__ mean, double eps) {
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < M; row += (int64_t)gridDim.x * blockDim.x)
@@ -449,6 +469,13 @@ cudaError_t launch_hankel_finish(const EpiArgs& a, bool hankel_src, const double
     const int grid = stream_grid(a.M, sm_count);
     if (hankel_src) hankel_finish_kernel<true><<<grid, 256, 0, st>>>(a, mean);
     else hankel_finish_kernel<false><<<grid, 256, 0, st>>>(a, mean);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dense_update(const double* D, double* A, const double* E, double* Y, double* Z, int64_t M, int64_t N,
+                                double mu, int nonnegA, double* zz, int sm_count, cudaStream_t st, int64_t* launches) {
+    dense_update_kernel<<<stream_grid(M * N, sm_count), 256, 0, st>>>(D, A, E, Y, Z, M * N, mu, nonnegA, zz);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -84,6 +84,9 @@ cudaError_t launch_scale_cols_floor(const double* V, const double* sigma, int n,
                                     double* sc_out, cudaStream_t st, int64_t* launches);
 cudaError_t launch_scale_cols_mul(const double* R, const double* sc, int n, double* K, cudaStream_t st,
                                   int64_t* launches);
+// B[:, c] = V[:, c] * f[c], c < cols   (n rows)
+cudaError_t launch_scale_cols_mulvec(const double* V, const double* f, int n, int cols, double* B, cudaStream_t st,
+                                     int64_t* launches);
 // C = A B for n x n column-major matrices
 cudaError_t launch_gemm_nn(const double* A, const double* B, int n, double* C, cudaStream_t st, int64_t* launches);
 
@@ -260,6 +263,9 @@ cudaError_t launch_transpose(const double* in, int64_t M, int64_t N, double* out
 // finish: A = soft_th(A_raw, eps, mean[r+c]); clamp; E from (D, A_prev, Y_prev); Z = D - A - E; Y += mu Z; ||Z||_F^2
 cudaError_t launch_hankel_finish(const EpiArgs& a, bool hankel_src, const double* mean, int sm_count, cudaStream_t st,
                                  int64_t* launches);
+// dense iterate: A = max(A,0) [nonnegA]; Z = (D - A) - E; Y += mu Z; *zz += ||Z||_F^2   (:217-222; all M x N, ld M)
+cudaError_t launch_dense_update(const double* D, double* A, const double* E, double* Y, double* Z, int64_t M, int64_t N,
+                                double mu, int nonnegA, double* zz, int sm_count, cudaStream_t st, int64_t* launches);
 // X[r,c] = soft_th(X[r,c], eps, mean[r+c]) in place (the final soft_hankel!(E, lambda/mu), :234-236)
 cudaError_t launch_soft_hankel_apply(double* X, int64_t M, int64_t N, const double* mean, double eps, int sm_count,
                                      cudaStream_t st, int64_t* launches);

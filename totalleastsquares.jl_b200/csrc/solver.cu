@@ -108,7 +108,7 @@ struct tlsq_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // output pass of the finalisation overlaps the full eigensolver
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_iter = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_iter = nullptr, ev_d2h = nullptr;
     int64_t launches = 0;
     cudaMemPool_t pool = nullptr;         // private stream-ordered pool (release threshold: keep everything)
     void* comm = nullptr;
@@ -237,6 +237,10 @@ struct RpcaOut {
     int64_t* sv = nullptr;  int64_t* iters_done = nullptr;  int32_t* converged = nullptr;  double* hist = nullptr;
     // lowrankfilter: anti-diagonal sums of the final (factored) A over this shard's Hankel rows [uh_r0, uh_r0 + M)
     double* uh_sum = nullptr;  int64_t uh_r0 = 0;  int64_t uh_Ns = 0;
+    // host-buffer entry points: pinned or pageable HOST destinations of A / E.  When set, their device->host copies are
+    // issued on the side stream as soon as the output pass has produced them, i.e. they overlap the eigensolver and the
+    // SVD refinement that still run on the main stream; *host_copied tells the caller that they were taken care of.
+    double* hA = nullptr;  double* hE = nullptr;  bool* host_copied = nullptr;
 };
 
 int gram_dense(tlsq_handle* h, const double* X, int64_t M, int64_t n, double* G);
@@ -884,6 +888,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     // ---- outputs (:238) ----------------------------------------------------------------------------------
     Phase ph_final(h, TLSQ_PHASE_FINALIZE);
     const bool want_svd = o.S || o.Vt || o.U;
+    bool d2h_pending = false;
     // The returned SVD is that of the LAST SVT input W_k (:194, 238): W_k is materialised once (the W buffer of the
     // two-kernel pipeline is free now).
     double* Wfin = nullptr;
@@ -917,6 +922,12 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
         }
         CK(cudaEventRecord(h->ev_join, ss));
         CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+        if (o.host_copied && (o.hA || o.hE)) {
+            if (o.hA && o.A) CK(cudaMemcpyAsync(o.hA, o.A, mn * 8, cudaMemcpyDeviceToHost, ss));
+            if (o.hE && o.E) CK(cudaMemcpyAsync(o.hE, o.E, mn * 8, cudaMemcpyDeviceToHost, ss));
+            CK(cudaEventRecord(h->ev_d2h, ss));
+            d2h_pending = true;
+        }
     } else {
         if (o.uh_sum) {
             // the rank estimate left the factored path: anti-diagonal sums from the dense A_k
@@ -969,6 +980,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
             CK(launch_gemm_any(Wfin, M, n, M, sqA, n, o.U, st, L));                      // U = W_k V diag(1/s)
         }
     }
+    if (d2h_pending) { CK(cudaStreamWaitEvent(st, h->ev_d2h, 0)); *o.host_copied = true; }
     CK(cudaStreamSynchronize(st));
     if (o.sv) {
         int64_t sv = svp_last;                                                           // :199-204
@@ -1021,6 +1033,7 @@ int rpca_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, const RpcaPa
     CK(launch_transpose(D, M, N, bDt.as<double>(), st, &h->launches));
     RpcaOut ot = o;
     ot.A = nullptr; ot.E = nullptr; ot.U = nullptr; ot.Vt = nullptr;
+    ot.hA = nullptr; ot.hE = nullptr; ot.host_copied = nullptr;       // outputs are transposed back first
     if (o.A) { CK(bAt.alloc(mn * 8, st)); ot.A = bAt.as<double>(); }
     if (o.E) { CK(bEt.alloc(mn * 8, st)); ot.E = bEt.as<double>(); }
     const int64_t d = M;                       // min(M, N)
@@ -1288,6 +1301,246 @@ int lowrankfilter_general_dev(tlsq_handle* h, const double* y, int64_t Ns, int64
     return TLSQ_OK;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// rpca with the reference's plugin callables svd / opnorm (src/robustPCA.jl:168-169; used at :177, :193-197, :225).
+// A Julia closure reaches this file as a C function pointer; the matrices cross the boundary in HOST memory, so every
+// call costs a device->host and a host->device copy: this is the reference's plugin hook, not the fast path.  The
+// iterate is dense, every step a plain kernel / GEMM; NULL callables use the built-in device implementations (full
+// Jacobi spectrum).  M x N of any orientation with min(M, N) <= kEigMaxN.
+// ----------------------------------------------------------------------------------------------------------
+struct EigScratch {            // n x n eigen workspace for the helpers below
+    DevBuf bG, bV, bLam, bE;
+    EigWork ew;
+    int n = 0;
+    int init(int nn, cudaStream_t st) {
+        n = nn;
+        CK(bG.alloc((size_t)n * n * 8, st)); CK(bV.alloc((size_t)n * n * 8, st)); CK(bLam.alloc((size_t)n * 8, st));
+        CK(bE.alloc(eig_work_doubles(n) * 8, st));
+        double* base = bE.as<double>();
+        const size_t np = (size_t)n + 34;
+        ew.X0 = base; base += (size_t)n * n;
+        ew.Xo = base; base += np * n;
+        ew.Vo = base; base += np * n;
+        ew.lam_raw = base; base += np;
+        ew.perm = reinterpret_cast<int*>(base); base += n;
+        ew.info = reinterpret_cast<int*>(base);
+        return TLSQ_OK;
+    }
+};
+
+// spectral norm of a dense M x N device matrix (Gram on the short side + full Jacobi); Xt: M x N scratch for wide X
+int device_opnorm(tlsq_handle* h, const double* X, int64_t M, int64_t N, double* Xt, EigScratch& es, double* out) {
+    cudaStream_t st = h->stream;
+    const double* T = X;
+    int64_t m = M, n = N;
+    if (M < N) { CK(launch_transpose(X, M, N, Xt, st, &h->launches)); T = Xt; m = N; n = M; }
+    CKR(gram_dense(h, T, m, n, es.bG.as<double>()));
+    CK(launch_eigh(es.bG.as<double>(), (int)n, nullptr, es.ew, es.bLam.as<double>(), es.bV.as<double>(), h->sm_count, st,
+                   &h->launches));
+    CK(cudaMemcpyAsync(h->h_pin, es.bLam.as<double>(), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out = sqrt(h->h_pin[0] > 0.0 ? h->h_pin[0] : 0.0);
+    return TLSQ_OK;
+}
+
+// thin SVD of a TALL dense device matrix W (M x n, M >= n) to LAPACK accuracy: eigenvectors of the Gram, then the
+// CholeskyQR2-style refinement of rpca_core (see there).  Outputs (device, nullable): U M x n, S n, Vt n x n.
+int svd_tall_dev(tlsq_handle* h, const double* W, int64_t M, int n, EigScratch& es, double* U, double* S, double* Vt) {
+    cudaStream_t st = h->stream;
+    int64_t* L = &h->launches;
+    DevBuf bC, bB, bK, bV2, bVf, bSc, bSig, bG2;
+    CK(bC.alloc((size_t)M * n * 8, st)); CK(bB.alloc((size_t)n * n * 8, st)); CK(bK.alloc((size_t)n * n * 8, st));
+    CK(bV2.alloc((size_t)n * n * 8, st)); CK(bVf.alloc((size_t)n * n * 8, st)); CK(bSc.alloc((size_t)n * 8, st));
+    CK(bSig.alloc((size_t)n * 8, st)); CK(bG2.alloc((size_t)n * n * 8, st));
+    double* G = es.bG.as<double>(); double* V = es.bV.as<double>(); double* lam = es.bLam.as<double>();
+    double* sig = bSig.as<double>();
+    DevBuf bF, bSvp;
+    CK(bF.alloc((size_t)n * 8, st)); CK(bSvp.alloc(16, st));
+    CKR(gram_dense(h, W, M, n, G));
+    CK(launch_eigh(G, n, nullptr, es.ew, lam, V, h->sm_count, st, L));
+    CK(launch_svt_post(lam, n, 0.0, 0, sig, bF.as<double>(), bSvp.as<int>(), st, L));           // sig = sqrt(lam)
+    CK(launch_scale_cols_floor(V, sig, n, 1.0e-8, bB.as<double>(), bSc.as<double>(), st, L));
+    CK(launch_gemm_any(W, M, n, M, bB.as<double>(), n, bC.as<double>(), st, L));
+    CKR(gram_dense(h, bC.as<double>(), M, n, bG2.as<double>()));
+    CK(launch_chol_upper(bG2.as<double>(), n, st, L));
+    CK(launch_scale_cols_mul(bG2.as<double>(), bSc.as<double>(), n, bK.as<double>(), st, L));
+    CK(launch_eigh(bK.as<double>(), n, nullptr, es.ew, sig, bV2.as<double>(), h->sm_count, st, L, nullptr, 1));
+    CK(launch_gemm_nn(V, bV2.as<double>(), n, bVf.as<double>(), st, L));
+    if (S) CK(cudaMemcpyAsync(S, sig, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    if (Vt) CK(launch_transpose(bVf.as<double>(), n, n, Vt, st, L));
+    if (U) {
+        CK(launch_scale_cols_inv(bVf.as<double>(), sig, n, bB.as<double>(), st, L));
+        CK(launch_gemm_any(W, M, n, M, bB.as<double>(), n, U, st, L));
+    }
+    CK(cudaStreamSynchronize(st));        // the temporaries above are released in stream order after this point
+    return TLSQ_OK;
+}
+
+int rpca_cb_host(tlsq_handle* h, const double* Dh, int64_t M, int64_t N, const RpcaParams& p, tlsq_svd_fn svd_fn,
+                 tlsq_opnorm_fn opn_fn, void* user, double* Ah, double* Eh, double* Uh, double* Sh, double* Vth,
+                 int64_t* sv_out, int64_t* iters_done, int32_t* converged, double* hist) {
+    CKR(check_rpca_args(M, N, p));
+    cudaStream_t st = h->stream;
+    int64_t* L = &h->launches;
+    const int sms = h->sm_count;
+    const int64_t d = M < N ? M : N;
+    if (d > kEigMaxN) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: min(M,N) = %lld exceeds the supported %d", (long long)d, kEigMaxN);
+    if (h->nranks > 1) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca with user callables is single-GPU (the callables see the whole matrix)");
+    const bool tall = M >= N;
+    const int n = (int)d;
+    const size_t mn = (size_t)M * N;
+    const int nonnegA = (p.flags & TLSQ_NONNEG_A) ? 1 : 0, nonnegE = (p.flags & TLSQ_NONNEG_E) ? 1 : 0;
+    const int nukeA = (p.flags & TLSQ_NO_NUKE_A) ? 0 : 1;
+    const bool hk = (p.flags & TLSQ_HANKEL) != 0;
+    DevBuf bD, bA, bE, bY, bZ, bW, bT, bXt, bUs, bVr, bMean, bScal, bSig, bF, bSvp, bB1;
+    CK(bD.alloc(mn * 8, st)); CK(bA.alloc(mn * 8, st)); CK(bE.alloc(mn * 8, st)); CK(bY.alloc(mn * 8, st));
+    CK(bZ.alloc(mn * 8, st)); CK(bW.alloc(mn * 8, st)); CK(bT.alloc(mn * 8, st)); CK(bXt.alloc(mn * 8, st));
+    CK(bUs.alloc((size_t)(M > N ? M : N) * n * 8, st)); CK(bVr.alloc((size_t)n * (M > N ? M : N) * 8, st));
+    CK(bMean.alloc((size_t)(M + N) * 8, st)); CK(bScal.alloc(64, st)); CK(bSig.alloc((size_t)n * 8, st));
+    CK(bF.alloc((size_t)n * 8, st)); CK(bSvp.alloc(16, st)); CK(bB1.alloc((size_t)n * n * 8, st));
+    double* D = bD.as<double>(); double* A = bA.as<double>(); double* E = bE.as<double>(); double* Y = bY.as<double>();
+    double* Z = bZ.as<double>(); double* W = bW.as<double>(); double* dscal = bScal.as<double>();
+    EigScratch es;
+    CKR(es.init(n, st));
+    std::vector<double> Zh(mn), Us((size_t)M * n), Ss(n), Vts((size_t)n * N), Usc((size_t)M * n), Vrc((size_t)n * N);
+    int64_t r_user = -1;                     // rank of the last user SVD (-1: the last SVD was the built-in one)
+    CK(cudaMemcpyAsync(D, Dh, mn * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(A, 0, mn * 8, st));
+    CK(cudaMemsetAsync(dscal, 0, 64, st));
+    // ---- setup (:174-185) ----
+    double norm2 = 0.0;
+    if (opn_fn) norm2 = opn_fn(user, Dh, M, N);                                          // opnorm(Y)::RT  :177
+    else CKR(device_opnorm(h, D, M, N, bXt.as<double>(), es, &norm2));
+    if (!(norm2 > 0.0) || norm2 != norm2) return set_err(TLSQ_ERR_ARG, "rpca: opnorm(D) returned %g", norm2);
+    CK(launch_maxabs(MatSrc{D, M}, false, M, N, dscal + 1, sms, st, L));
+    CK(cudaMemcpyAsync(h->h_pin, dscal + 1, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double norminf = h->h_pin[0] / p.lambda;
+    const double dual_norm = norm2 > norminf ? norm2 : norminf;
+    const double d_norm = norm2;
+    double mu = 1.25 / norm2;
+    const double mubar = mu * 1.0e7;
+    CK(launch_init_ya(MatSrc{D, M}, false, M, N, dual_norm, Y, nullptr, nullptr, 1.0 / mu, p.lambda / mu, nonnegE, sms, st, L));
+    int64_t sv = 10, k_done = 0;
+    int conv = 0, svp = 0;
+    // built-in SVT of the current W (tall orientation T: m x n): A_T = T V_r f V_r'
+    auto builtin_svt = [&](double im) -> int {
+        const double* T = W;
+        int64_t m = M;
+        if (!tall) { CK(launch_transpose(W, M, N, bXt.as<double>(), st, L)); T = bXt.as<double>(); m = N; }
+        CKR(gram_dense(h, T, m, n, es.bG.as<double>()));
+        CK(launch_eigh(es.bG.as<double>(), n, nullptr, es.ew, es.bLam.as<double>(), es.bV.as<double>(), sms, st, L));
+        CK(launch_svt_post(es.bLam.as<double>(), n, im, nukeA, bSig.as<double>(), bF.as<double>(), bSvp.as<int>(), st, L));
+        CK(cudaMemcpyAsync(h->h_pin, bSvp.as<int>(), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(&svp, h->h_pin, 4);
+        if (svp == 0) { CK(cudaMemsetAsync(A, 0, mn * 8, st)); return TLSQ_OK; }
+        // B1 = V_r diag(f) (n x svp): scale the leading columns; Ttmp = T B1 (m x svp); A_T = Ttmp V_r'
+        CK(launch_scale_cols_mulvec(es.bV.as<double>(), bF.as<double>(), n, svp, bB1.as<double>(), st, L));
+        CK(launch_gemm_any(T, m, n, m, bB1.as<double>(), svp, bUs.as<double>(), st, L));
+        CK(launch_transpose(es.bV.as<double>(), n, svp, bVr.as<double>(), st, L));       // V_r' : svp x n
+        double* AT = tall ? A : bT.as<double>();
+        CK(launch_gemm_any(bUs.as<double>(), m, svp, m, bVr.as<double>(), n, AT, st, L));
+        if (!tall) CK(launch_transpose(AT, N, M, A, st, L));
+        return TLSQ_OK;
+    };
+    for (int64_t k = 1; k <= p.iters; ++k) {
+        const double im = 1.0 / mu, eps = p.lambda / mu;
+        CK(launch_compute_e(MatSrc{D, M}, false, M, N, A, Y, im, eps, nonnegE, E, sms, st, L, W));     // :188-192
+        if (svd_fn && k > 1) {                                                                       // svd(Z, sv)  :196
+            CK(cudaMemcpyAsync(Zh.data(), W, mn * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const int64_t r = svd_fn(user, Zh.data(), M, N, sv, Us.data(), Ss.data(), Vts.data());
+            if (r < 0 || r > d) return set_err(TLSQ_ERR_ARG, "rpca: the svd callable returned rank %lld (expected 0..%lld)", (long long)r, (long long)d);
+            r_user = r;
+            svp = 0;
+            for (int64_t i = 0; i < r; ++i) svp += (Ss[i] >= im) ? 1 : 0;                            // :198
+            if (svp == 0) {
+                CK(cudaMemsetAsync(A, 0, mn * 8, st));
+            } else {
+                // A = U[:,1:svp] diag(S - 1/mu) Vt[1:svp,:]   (:207-208; no shift when nukeA=false :211-212); Vt is r x N
+                for (int c = 0; c < svp; ++c) {
+                    const double f = nukeA ? Ss[c] - im : Ss[c];
+                    for (int64_t i = 0; i < M; ++i) Usc[(size_t)c * M + i] = Us[(size_t)c * M + i] * f;
+                }
+                for (int64_t j = 0; j < N; ++j)
+                    for (int c = 0; c < svp; ++c) Vrc[(size_t)j * svp + c] = Vts[(size_t)j * r + c];
+                CK(cudaMemcpyAsync(bUs.as<double>(), Usc.data(), (size_t)M * svp * 8, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(bVr.as<double>(), Vrc.data(), (size_t)svp * N * 8, cudaMemcpyHostToDevice, st));
+                CK(launch_gemm_any(bUs.as<double>(), M, svp, M, bVr.as<double>(), (int)N, A, st, L));
+            }
+        } else {
+            r_user = -1;
+            CKR(builtin_svt(im));                                                                    // svd!(Z)  :194
+        }
+        sv = svp;                                                                                    // :199-204
+        if (sv < 1) sv = 1;
+        if (p.maxrank > 0 && sv > p.maxrank) sv = p.maxrank;
+        if (hk) {                                                                                    // :214-216
+            CK(launch_unhankel(A, M, N, 1, M + N - 1, bMean.as<double>(), st, L));
+            CK(launch_soft_hankel_apply(A, M, N, bMean.as<double>(), eps, sms, st, L));
+        }
+        CK(cudaMemsetAsync(dscal, 0, 8, st));
+        CK(launch_dense_update(D, A, E, Y, Z, M, N, mu, nonnegA, dscal, sms, st, L));                // :217-222
+        mu = fmin(mu * p.rho, mubar);                                                                // :223
+        double cost = 0.0;
+        if (opn_fn) {                                                                                // opnorm(Z)  :225
+            CK(cudaMemcpyAsync(Zh.data(), Z, mn * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            cost = opn_fn(user, Zh.data(), M, N) / d_norm;
+        } else {
+            CKR(device_opnorm(h, Z, M, N, bXt.as<double>(), es, &cost));
+            cost /= d_norm;
+        }
+        if (hist) { hist[3 * (k - 1)] = (double)k; hist[3 * (k - 1) + 1] = (double)svp; hist[3 * (k - 1) + 2] = cost; }
+        k_done = k;
+        if (cost < p.tol) { conv = 1; break; }                                                       // :228
+    }
+    if (hk) {                                                                                        // :234-236
+        CK(launch_unhankel(E, M, N, 1, M + N - 1, bMean.as<double>(), st, L));
+        CK(launch_soft_hankel_apply(E, M, N, bMean.as<double>(), p.lambda / mu, sms, st, L));
+    }
+    if (Ah) CK(cudaMemcpyAsync(Ah, A, mn * 8, cudaMemcpyDeviceToHost, st));
+    if (Eh) CK(cudaMemcpyAsync(Eh, E, mn * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // s: the SVD object of the LAST SVT input (:238) -- the user's, or the built-in one to LAPACK accuracy
+    if (Uh || Sh || Vth) {
+        if (r_user >= 0) {
+            if (Uh) { memset(Uh, 0, (size_t)M * d * 8); memcpy(Uh, Us.data(), (size_t)M * r_user * 8); }
+            if (Sh) { memset(Sh, 0, (size_t)d * 8); memcpy(Sh, Ss.data(), (size_t)r_user * 8); }
+            if (Vth) {
+                memset(Vth, 0, (size_t)d * N * 8);
+                for (int64_t j = 0; j < N; ++j)
+                    for (int64_t c = 0; c < r_user; ++c) Vth[(size_t)j * d + c] = Vts[(size_t)j * r_user + c];
+            }
+        } else {
+            DevBuf bU, bS, bVt;
+            const int64_t m = tall ? M : N;
+            CK(bU.alloc((size_t)m * n * 8, st)); CK(bS.alloc((size_t)n * 8, st)); CK(bVt.alloc((size_t)n * n * 8, st));
+            const double* T = W;
+            if (!tall) { CK(launch_transpose(W, M, N, bXt.as<double>(), st, L)); T = bXt.as<double>(); }
+            CKR(svd_tall_dev(h, T, m, n, es, bU.as<double>(), bS.as<double>(), bVt.as<double>()));
+            if (Sh) CK(cudaMemcpyAsync(Sh, bS.as<double>(), (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            if (tall) {
+                if (Uh) CK(cudaMemcpyAsync(Uh, bU.as<double>(), (size_t)M * n * 8, cudaMemcpyDeviceToHost, st));
+                if (Vth) CK(cudaMemcpyAsync(Vth, bVt.as<double>(), (size_t)n * N * 8, cudaMemcpyDeviceToHost, st));
+            } else {
+                // W' = U_t S V_t'  =>  W = V_t S U_t':  U = V_t (M x d) = (Vt_t)',  Vt = U_t' (d x N)
+                if (Uh) { CK(launch_transpose(bVt.as<double>(), n, n, bB1.as<double>(), st, L));
+                          CK(cudaMemcpyAsync(Uh, bB1.as<double>(), (size_t)M * n * 8, cudaMemcpyDeviceToHost, st)); }
+                if (Vth) { CK(launch_transpose(bU.as<double>(), N, n, bT.as<double>(), st, L));
+                           CK(cudaMemcpyAsync(Vth, bT.as<double>(), (size_t)n * N * 8, cudaMemcpyDeviceToHost, st)); }
+            }
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    if (sv_out) *sv_out = sv;
+    if (iters_done) *iters_done = k_done;
+    if (converged) *converged = conv;
+    return TLSQ_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
@@ -1328,6 +1581,7 @@ int tlsq_create(int device, tlsq_handle** out) {
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_iter, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
     CK(cudaMallocHost(&h->h_pin, 64 * sizeof(double)));
     // keep freed blocks cached between solves -- in a pool of our own (the default pool's attributes are left alone)
     {
@@ -1357,6 +1611,7 @@ int tlsq_destroy(tlsq_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_iter) cudaEventDestroy(h->ev_iter);
+    if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); if (t_pool == h->pool) t_pool = nullptr; }
     delete h;
@@ -1453,14 +1708,26 @@ int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double 
     o.A = A ? bA.as<double>() : nullptr; o.E = E ? bE.as<double>() : nullptr; o.U = U ? bU.as<double>() : nullptr;
     o.S = S ? bS.as<double>() : nullptr; o.Vt = Vt ? bVt.as<double>() : nullptr;
     o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
+    bool host_copied = false;                  // A / E went to the host while the SVD was still being computed
+    o.hA = A; o.hE = E; o.host_copied = &host_copied;
     CKR(rpca_dev(h, bD.as<double>(), M, N, p, o));
-    if (A) CK(cudaMemcpyAsync(A, o.A, mn * 8, cudaMemcpyDeviceToHost, st));
-    if (E) CK(cudaMemcpyAsync(E, o.E, mn * 8, cudaMemcpyDeviceToHost, st));
+    if (A && !host_copied) CK(cudaMemcpyAsync(A, o.A, mn * 8, cudaMemcpyDeviceToHost, st));
+    if (E && !host_copied) CK(cudaMemcpyAsync(E, o.E, mn * 8, cudaMemcpyDeviceToHost, st));
     if (U) CK(cudaMemcpyAsync(U, o.U, (size_t)M * d * 8, cudaMemcpyDeviceToHost, st));
     if (S) CK(cudaMemcpyAsync(S, o.S, (size_t)d * 8, cudaMemcpyDeviceToHost, st));
     if (Vt) CK(cudaMemcpyAsync(Vt, o.Vt, (size_t)d * N * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return TLSQ_OK;
+}
+
+int tlsq_rpca_cb_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double lambda, int64_t maxrank, int64_t iters,
+                     double tol, double rho, uint32_t flags, tlsq_svd_fn svd_fn, tlsq_opnorm_fn opnorm_fn, void* user,
+                     double* A, double* E, double* U, double* S, double* Vt, int64_t* sv, int64_t* iters_done,
+                     int32_t* converged, double* hist) {
+    CKR(use_device(h));
+    if (!D) return set_err(TLSQ_ERR_ARG, "rpca: D is NULL");
+    RpcaParams p{lambda, tol, rho, maxrank, iters, flags};
+    return rpca_cb_host(h, D, M, N, p, svd_fn, opnorm_fn, user, A, E, U, S, Vt, sv, iters_done, converged, hist);
 }
 
 // ---- lowrankfilter ---------------------------------------------------------------------------------------
