@@ -307,9 +307,19 @@ enum GaMode : int {
     GA_PASS  = 2    // mu_i = (sum_n s[n] X[i,n]) / sumw ; t[n] += sum_i X[i,n] mu_i ; t[N] += sum_i mu_i^2
 };                  //                                                          (:291-294, 308-316 in ONE sweep)
 // X: d x N (ld), vec: q (GA_DOTS, length d) or mu out (GA_PASS, length d); s: N sign weights; sumw: device scalar
+// part (optional, ga_partial_doubles(sm_count) doubles): workspace of the TMA-staged kernel (N <= 256); with it the
+// column sums are reduced in fixed order (deterministic), without it the register-prefetch kernel with atomics runs
 cudaError_t launch_ga_sweep(GaMode mode, const double* X, int64_t d, int64_t N, int64_t ld, double* vec,
                             const double* s, const double* sumw, double* t, int sm_count, cudaStream_t st,
-                            int64_t* launches);
+                            int64_t* launches, double* part = nullptr);
+size_t ga_partial_doubles(int sm_count);
+// fused tail / head of two components (TMA kernel, same eligibility; cudaErrorNotSupported otherwise): X -= q xs' in
+// place (:272); n2[n] += |x_n|^2 of the deflated columns (:265); t2[n] += x_n'q2 when q2 != null (:292)
+cudaError_t launch_ga_deflate_fused(double* X, int64_t d, int64_t N, int64_t ld, const double* q, const double* xs,
+                                    const double* q2, double* n2, double* t2, double* part, int sm_count,
+                                    cudaStream_t st, int64_t* launches);
+// xs[n] = t[n] / sqrt(t[N])   (q'x_n from the dot products x_n'mu of the converged iteration, q = mu/|mu|)
+cudaError_t launch_ga_xs(const double* t, int64_t N, double* xs, cudaStream_t st, int64_t* launches);
 // robust entry-wise averages (:323-333, :349-357): out[j] (length d) from a per-row sort over the N observations;
 // kind 1 = trimmed mean (fraction P dropped on each side), 2 = median.  N is limited by shared memory (~600).
 cudaError_t launch_ga_robust(const double* X, int64_t d, int64_t N, int64_t ld, const double* sgn, const double* n2,
@@ -317,9 +327,9 @@ cudaError_t launch_ga_robust(const double* X, int64_t d, int64_t N, int64_t ld, 
 // s[n] = sign(t[n]) (0 if norms[n]==0), sumw = sum_n s[n]*norms[n]            (:292, :310-312)
 cudaError_t launch_ga_signs(const double* t, const double* norms2, int64_t N, double* s, double* sumw,
                             cudaStream_t st, int64_t* launches);
-// q = mu / sqrt(mm);  dq2 += sum (q - qold)^2;  qold <- q   (:295-296, 302)   (mm, dq2 device scalars)
-cudaError_t launch_ga_update(const double* mu, const double* mm, int64_t d, double* q, double* dq2, int sm_count,
-                             cudaStream_t st, int64_t* launches);
+// qnew = mu / sqrt(mm);  dq2 += sum (qnew - qold)^2   (:295-296, 302)   (mm, dq2 device scalars; qnew may alias qold)
+cudaError_t launch_ga_update(const double* mu, const double* mm, int64_t d, const double* qold, double* qnew, double* dq2,
+                             int sm_count, cudaStream_t st, int64_t* launches);
 // ss += sum_i v[i]^2 ;  scale: v *= 1/sqrt(ss)
 cudaError_t launch_vec_sumsq(const double* v, int64_t d, double* ss, int sm_count, cudaStream_t st,
                              int64_t* launches);

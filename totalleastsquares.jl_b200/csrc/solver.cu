@@ -1061,35 +1061,59 @@ int rpca_ga_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r
     const int sms = h->sm_count;
     int64_t* L = &h->launches;
     const size_t dn = (size_t)d * N;
-    DevBuf bX, bT, bN2, bS, bQ, bMu, bXs, bSc;
-    CK(bX.alloc(dn * 8, st)); CK(bT.alloc((size_t)(N + 1) * 8, st)); CK(bN2.alloc((size_t)N * 8, st));
-    CK(bS.alloc((size_t)N * 8, st)); CK(bQ.alloc((size_t)d * 8, st)); CK(bMu.alloc((size_t)d * 8, st));
-    CK(bXs.alloc((size_t)N * 8, st)); CK(bSc.alloc(8 * 8, st));
-    double* Xw = bX.as<double>(); double* t = bT.as<double>(); double* n2 = bN2.as<double>();
-    double* s = bS.as<double>(); double* q = bQ.as<double>(); double* mu = bMu.as<double>();
-    double* xs = bXs.as<double>(); double* sc = bSc.as<double>();   // sc[0] = sumw, sc[1] = ss, sc[2] = dq2
+    DevBuf bX, bT, bT2, bN2, bS, bQ, bQ2, bQn, bMu, bXs, bSc, bPart;
+    CK(bX.alloc(dn * 8, st)); CK(bT.alloc((size_t)(N + 1) * 8, st)); CK(bT2.alloc((size_t)(N + 1) * 8, st));
+    CK(bN2.alloc((size_t)N * 8, st));
+    CK(bS.alloc((size_t)N * 8, st)); CK(bQ.alloc((size_t)d * 8, st)); CK(bQ2.alloc((size_t)d * 8, st));
+    CK(bQn.alloc((size_t)d * 8, st));
+    CK(bMu.alloc((size_t)d * 8, st)); CK(bXs.alloc((size_t)N * 8, st)); CK(bSc.alloc(8 * 8, st));
+    CK(bPart.alloc(ga_partial_doubles(sms) * 8, st));
+    double* Xw = bX.as<double>(); double* n2 = bN2.as<double>();
+    double* tb[2] = {bT.as<double>(), bT2.as<double>()};           // dot products: iteration `it` writes tb[it & 1]
+    double* s = bS.as<double>(); double* mu = bMu.as<double>();
+    double* qb[2] = {bQ.as<double>(), bQ2.as<double>()};            // q ping-pong: the run-ahead iteration must not clobber
+    double* qnext = bQn.as<double>();                               // normalised start vector of the next component
+    double* xs = bXs.as<double>(); double* sc = bSc.as<double>();   // sc[0] = sumw, sc[1] = ss, sc[2], sc[3] = dq2 slots
+    double* part = bPart.as<double>();
     double* hp = h->h_pin;
+    const bool no_ahead = getenv("TLSQ_NO_RUNAHEAD") != nullptr;
+    const bool no_fuse = getenv("TLSQ_GA_NO_FUSE") != nullptr;
     CK(cudaMemcpyAsync(Xw, X, dn * 8, cudaMemcpyDeviceToDevice, st));                    // X = copy(X)   :257
 
-    for (int64_t i = 0; i < r; ++i) {                                                    // :263
-        CK(cudaMemsetAsync(n2, 0, (size_t)N * 8, st));
-        CK(launch_ga_sweep(GA_NORMS, Xw, d, N, d, nullptr, nullptr, nullptr, n2, sms, st, L));   // :265
-        CKR(allreduce(h, n2, (size_t)N, kNcclSum));
-        // q = randn(d); q ./= norm(q)   (:286-287) -- the draw comes from the caller
-        CK(cudaMemsetAsync(sc, 0, 8 * 8, st));
-        CK(launch_vec_sumsq(q0 + i * d, d, sc + 1, sms, st, L));
+    // q = randn(d); q ./= norm(q)   (:286-287) -- the draw comes from the caller
+    auto normalise_start = [&](int64_t comp, double* out) -> int {
+        CK(cudaMemsetAsync(sc + 1, 0, 8, st));
+        CK(launch_vec_sumsq(q0 + comp * d, d, sc + 1, sms, st, L));
         CKR(allreduce(h, sc + 1, 1, kNcclSum));
-        CK(launch_vec_scale_rsqrt(q0 + i * d, sc + 1, d, q, sms, st, L));
-        CK(cudaMemsetAsync(t, 0, (size_t)(N + 1) * 8, st));
-        CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, q, nullptr, nullptr, t, sms, st, L));   // first U[:,n]'q  :292
-        CKR(allreduce(h, t, (size_t)N, kNcclSum));
-        int64_t its = 0;
-        for (int64_t it = 1; it <= iters; ++it) {                                        // :290
-            CK(launch_ga_signs(t, n2, N, s, sc, st, L));
+        CK(launch_vec_scale_rsqrt(q0 + comp * d, sc + 1, d, out, sms, st, L));
+        return TLSQ_OK;
+    };
+    bool head_ready = false;      // n2 and tb[0] of this component already came with the previous component's deflation
+    for (int64_t i = 0; i < r; ++i) {                                                    // :263
+        int cq = 0;                                                                      // qb[cq] = current q
+        if (!head_ready) {
+            CK(cudaMemsetAsync(n2, 0, (size_t)N * 8, st));
+            CK(launch_ga_sweep(GA_NORMS, Xw, d, N, d, nullptr, nullptr, nullptr, n2, sms, st, L, part));   // :265
+            CKR(allreduce(h, n2, (size_t)N, kNcclSum));
+            CKR(normalise_start(i, qb[0]));
+            CK(cudaMemsetAsync(tb[0], 0, (size_t)(N + 1) * 8, st));
+            CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, qb[0], nullptr, nullptr, tb[0], sms, st, L, part));   // U[:,n]'q  :292
+            CKR(allreduce(h, tb[0], (size_t)N, kNcclSum));
+        } else {
+            CK(cudaMemcpyAsync(qb[0], qnext, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        head_ready = false;
+        // One Grassmann iteration on the device (:291-296): signs from the dot products of the previous sweep (tb[(it-1)&1]),
+        // one sweep (mu, next dot products into tb[it&1], ||mu||^2), q_new into the OTHER q buffer, ||q_new - q||^2
+        // into slot `it & 1`.
+        auto enqueue_iteration = [&](int64_t it, int from) -> int {
+            const double* tin = tb[(it - 1) & 1];
+            double* t = tb[it & 1];
+            CK(launch_ga_signs(tin, n2, N, s, sc, st, L));
             CK(cudaMemsetAsync(t, 0, (size_t)(N + 1) * 8, st));
             if (mu_kind == 0) {
                 Phase ph(h, TLSQ_PHASE_GA_SWEEP);
-                CK(launch_ga_sweep(GA_PASS, Xw, d, N, d, mu, s, sc, t, sms, st, L));     // :291-294 in one sweep
+                CK(launch_ga_sweep(GA_PASS, Xw, d, N, d, mu, s, sc, t, sms, st, L, part));   // :291-294 in one sweep
             } else {
                 // robust entry-wise average (:323-333 / :349-357): a per-row sort over the observations (rows are local
                 // to a shard), then ||mu||^2 and the dot products of the NEXT iteration with q = mu/||mu|| -- the sign
@@ -1097,23 +1121,64 @@ int rpca_ga_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r
                 Phase ph(h, TLSQ_PHASE_GA_SWEEP);
                 CK(launch_ga_robust(Xw, d, N, d, s, n2, mu_kind, mu_p, mu, sms, st, L));
                 CK(launch_vec_sumsq(mu, d, t + N, sms, st, L));
-                CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, mu, nullptr, nullptr, t, sms, st, L));
+                CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, mu, nullptr, nullptr, t, sms, st, L, part));
             }
             CKR(allreduce(h, t, (size_t)(N + 1), kNcclSum));
-            CK(cudaMemsetAsync(sc + 2, 0, 8, st));
-            CK(launch_ga_update(mu, t + N, d, q, sc + 2, sms, st, L));                   // :295-296, 302
-            CKR(allreduce(h, sc + 2, 1, kNcclSum));
-            CK(cudaMemcpyAsync(hp, sc + 2, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            double* dq = sc + 2 + (it & 1);
+            CK(cudaMemsetAsync(dq, 0, 8, st));
+            CK(launch_ga_update(mu, t + N, d, qb[from], qb[from ^ 1], dq, sms, st, L));  // :295-296, 302
+            CKR(allreduce(h, dq, 1, kNcclSum));
+            CK(cudaMemcpyAsync(hp + (it & 1), dq, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(it & 1 ? h->ev_iter : h->ev_d2h, st));
+            return TLSQ_OK;
+        };
+        // The host only needs ||q_new - q|| to decide when to stop (:298): while it waits for iteration `it`, iteration
+        // `it + 1` is already enqueued (run-ahead), so the GPU never idles on the host round trip; if `it` turns out to
+        // be the last one the extra iteration is discarded (q and the dot products of iteration `it` live in their own
+        // buffers).  Close to the tolerance (last step within 16x) the loop stops running ahead: no wasted sweep.
+        int64_t its = 0;
+        double dq_prev = 1.0e300;
+        CKR(enqueue_iteration(1, cq));
+        for (int64_t it = 1; it <= iters; ++it) {                                        // :290
+            const int res = cq ^ 1;                     // buffer that iteration `it` writes
+            const bool ahead = !no_ahead && it < iters && !(dq_prev < 16.0 * tol);
+            if (ahead) CKR(enqueue_iteration(it + 1, res));
+            CK(cudaEventSynchronize(it & 1 ? h->ev_iter : h->ev_d2h));
             its = it;
-            if (sqrt(hp[0]) < tol) break;                                                // :298
+            cq = res;
+            dq_prev = sqrt(hp[it & 1]);
+            if (dq_prev < tol) break;                                                    // :298
+            if (!ahead && it < iters) CKR(enqueue_iteration(it + 1, cq));
         }
         if (iters_done) iters_done[i] = its;
+        double* q = qb[cq];
+        double* tl = tb[its & 1];                                                        // x_n'mu and ||mu||^2 of the last iteration
         CK(cudaMemcpyAsync(Q + i * d, q, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));  // :269
-        CK(cudaMemsetAsync(xs, 0, (size_t)N * 8, st));
-        CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, q, nullptr, nullptr, xs, sms, st, L));  // Xs1 = q'X   :271
-        CKR(allreduce(h, xs, (size_t)N, kNcclSum));
-        CK(launch_ga_deflate(Xw, d, N, d, q, xs, sms, st, L));                           // :272
+        if (i + 1 == r) break;                          // X is a private copy: deflating after the last component is moot
+        // Xs1 = q'X (:271) = (X'mu) / ||mu|| -- already known from the last sweep, no extra pass over X
+        bool fused_done = false;
+        if (!no_fuse) {
+            CK(launch_ga_xs(tl, N, xs, st, L));
+            CKR(normalise_start(i + 1, qnext));
+            CK(cudaMemsetAsync(n2, 0, (size_t)N * 8, st));
+            CK(cudaMemsetAsync(tb[0], 0, (size_t)(N + 1) * 8, st));
+            // X -= q Xs1 (:272) fused with the norms (:265) and first dot products (:292) of the next component
+            cudaError_t fe = launch_ga_deflate_fused(Xw, d, N, d, q, xs, qnext, n2, tb[0], part, sms, st, L);
+            if (fe == cudaSuccess) {
+                CKR(allreduce(h, n2, (size_t)N, kNcclSum));
+                CKR(allreduce(h, tb[0], (size_t)N, kNcclSum));
+                fused_done = true;
+                head_ready = true;
+            } else if (fe != cudaErrorNotSupported) {
+                CK(fe);
+            }
+        }
+        if (!fused_done) {
+            CK(cudaMemsetAsync(xs, 0, (size_t)N * 8, st));
+            CK(launch_ga_sweep(GA_DOTS, Xw, d, N, d, q, nullptr, nullptr, xs, sms, st, L, part));  // Xs1 = q'X   :271
+            CKR(allreduce(h, xs, (size_t)N, kNcclSum));
+            CK(launch_ga_deflate(Xw, d, N, d, q, xs, sms, st, L));                       // :272
+        }
     }
     CK(cudaStreamSynchronize(st));
     return TLSQ_OK;
