@@ -154,7 +154,7 @@ int tlsq_rpca_ga_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, 
 
 /* rpca_ga with the reference's pluggable robust averages (keyword mu, :255,294): mu_kind 0 = mu! (:308-316),
  * 1 = entrywise_trimmed_mean(s, w, U, P = mu_p) (:323-333), 2 = entrywise_median (:349-357).  A per-row sort over the N
- * observations (N <= 1024).  Rows may be sharded exactly like tlsq_rpca_ga_f64.                                    */
+ * observations (N <= 16384; beyond 1024 a slower one-row-per-CTA sort).  Rows may be sharded like tlsq_rpca_ga_f64.   */
 int tlsq_rpca_ga_mu_f64(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0,
                         double tol, int64_t iters, int mu_kind, double mu_p, double* Q, int64_t* iters_done);
 int tlsq_rpca_ga_mu_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t N, int64_t r, const double* q0,

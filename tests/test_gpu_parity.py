@@ -340,7 +340,7 @@ def test_rpca_ga_parity(d, N, r):
     assert np.linalg.norm(Q.T @ Q - np.eye(r)) < SQRT_EPS                 # test/runtests.jl:453
 
 
-@pytest.mark.parametrize("d,N,r", [(10, 1000, 3), (3000, 256, 3), (517, 100, 2)])
+@pytest.mark.parametrize("d,N,r", [(10, 1000, 3), (3000, 256, 3), (517, 100, 2), (40, 3000, 2)])
 def test_rpca_ga_robust_averages(d, N, r):
     """rpca_ga(...; μ = entrywise_trimmed_mean / entrywise_median) (src/robustPCA.jl:323-357, test/runtests.jl:491-523):
     per-row sorts on the GPU against the oracle restatement, same start vectors."""

@@ -438,6 +438,71 @@ ga_robust_kernel(const double* __restrict__ X, int64_t d, int N, int NP2, int RT
     }
 }
 
+// Long observation axes (1024 < N <= 16384): one CTA sorts one row at a time, keys and indices of the whole row in
+// shared memory (block-wide bitonic network), weights and norms through the read-only path.  Same selection rules as
+// ga_robust_kernel; a slow path for shapes the reference's tests never reach, but the result is defined for them.
+__global__ void __launch_bounds__(512)
+ga_robust_big_kernel(const double* __restrict__ X, int64_t d, int N, int NP2, int64_t ld, const double* __restrict__ sgn,
+                     const double* __restrict__ n2, int kind, int lo, int hi, double* __restrict__ out) {
+    extern __shared__ double smb[];
+    double* kk = smb;                                     // [NP2]
+    int* ii = reinterpret_cast<int*>(kk + NP2);           // [NP2]
+    __shared__ double rn[16], rd[16];
+    const int tid = threadIdx.x;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t row = blockIdx.x; row < d; row += gridDim.x) {
+        __syncthreads();
+        for (int n = tid; n < NP2; n += blockDim.x) {
+            double u = INF;
+            if (n < N) {
+                const double nr = sqrt(__ldg(n2 + n));
+                u = __ldg(X + (int64_t)n * ld + row) / nr;                       // U[j,n] = X[j,n] / Xnorms[n]   :266
+                if (kind == 2) u = (__ldg(sgn + n) * nr) * u;
+            }
+            kk[n] = u;
+            ii[n] = n;
+        }
+        __syncthreads();
+        for (int k = 2; k <= NP2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < NP2 / 2; t += blockDim.x) {
+                    const int a = 2 * t - (t & (j - 1));
+                    const int b = a + j;
+                    const bool up = (a & k) == 0;
+                    const double ka = kk[a], kb = kk[b];
+                    const int ia = ii[a], ib = ii[b];
+                    const bool gt = (ka > kb) || (ka == kb && ia > ib);
+                    if (gt == up) { kk[a] = kb; kk[b] = ka; ii[a] = ib; ii[b] = ia; }
+                }
+                __syncthreads();
+            }
+        if (kind == 1) {
+            double num = 0.0, den = 0.0;
+            for (int p = lo + tid; p < hi; p += blockDim.x) {
+                const int n = ii[p];
+                const double w = __ldg(sgn + n) * sqrt(__ldg(n2 + n));
+                num = fma(w, kk[p], num);
+                den += w;
+            }
+            num = warp_sum(num);
+            den = warp_sum(den);
+            if ((tid & 31) == 0) { rn[tid >> 5] = num; rd[tid >> 5] = den; }
+            __syncthreads();
+            if (tid == 0) {
+                double a = 0.0, b = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += rn[w]; b += rd[w]; }
+                out[row] = a / b;
+            }
+        } else if (tid == 0) {
+            const int m = ii[N / 2 - 1];
+            const double nr = sqrt(__ldg(n2 + m));
+            const double w = __ldg(sgn + m) * nr;
+            const double u = __ldg(X + (int64_t)m * ld + row) / nr;
+            out[row] = (w > 0.0 ? 1.0 : (w < 0.0 ? -1.0 : 0.0)) * u;
+        }
+    }
+}
+
 }  // namespace
 
 size_t ga_partial_doubles(int sm_count) { return (size_t)sm_count * GA_PSTRIDE; }
@@ -592,7 +657,18 @@ cudaError_t launch_ga_robust(const double* X, int64_t d, int64_t N, int64_t ld, 
     };
     if (need(rt) > (size_t)220 * 1024) rt = 8;
     const size_t smem = need(rt);
-    if (smem > (size_t)220 * 1024) return cudaErrorInvalidValue;          // N > ~1024 observations
+    const int lo_ = (int)floor(P * (double)N), hi_ = (int)floor((1.0 - P) * (double)N);    // :325
+    if (smem > (size_t)220 * 1024) {
+        // long observation axis: one row per CTA, the whole row sorted in shared memory (N <= kGaRobustMaxN)
+        const size_t smb = (size_t)np2 * (sizeof(double) + sizeof(int));
+        if (N > kGaRobustMaxN || smb > (size_t)220 * 1024) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(ga_robust_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+        if (e != cudaSuccess) return e;
+        int64_t blocks = d < (int64_t)sm_count ? d : (int64_t)sm_count;
+        ga_robust_big_kernel<<<(unsigned)blocks, 512, smb, st>>>(X, d, (int)N, np2, ld, sgn, n2, kind, lo_, hi_, out);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(ga_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -321,7 +321,9 @@ cudaError_t launch_ga_deflate_fused(double* X, int64_t d, int64_t N, int64_t ld,
 // xs[n] = t[n] / sqrt(t[N])   (q'x_n from the dot products x_n'mu of the converged iteration, q = mu/|mu|)
 cudaError_t launch_ga_xs(const double* t, int64_t N, double* xs, cudaStream_t st, int64_t* launches);
 // robust entry-wise averages (:323-333, :349-357): out[j] (length d) from a per-row sort over the N observations;
-// kind 1 = trimmed mean (fraction P dropped on each side), 2 = median.  N is limited by shared memory (~600).
+// kind 1 = trimmed mean (fraction P dropped on each side), 2 = median.  N <= 1024: 8 / 32 rows per tile, one warp per
+// row; up to kGaRobustMaxN observations: one CTA per row (slow path).
+constexpr int kGaRobustMaxN = 16384;
 cudaError_t launch_ga_robust(const double* X, int64_t d, int64_t N, int64_t ld, const double* sgn, const double* n2,
                              int kind, double P, double* out, int sm_count, cudaStream_t st, int64_t* launches);
 // s[n] = sign(t[n]) (0 if norms[n]==0), sumw = sum_n s[n]*norms[n]            (:292, :310-312)

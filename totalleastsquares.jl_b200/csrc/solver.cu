@@ -1846,7 +1846,7 @@ int tlsq_rpca_ga_mu_f64_dev(tlsq_handle* h, const double* X, int64_t d, int64_t 
                             double tol, int64_t iters, int mu_kind, double mu_p, double* Q, int64_t* iters_done) {
     CKR(use_device(h));
     if (mu_kind < 0 || mu_kind > 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: mu_kind must be 0 (mean), 1 (trimmed mean) or 2 (median)");
-    if (mu_kind && N > 1024) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most 1024 observations");
+    if (mu_kind && N > kGaRobustMaxN) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most %d observations", kGaRobustMaxN);
     if (mu_kind == 2 && N < 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: entrywise_median needs at least 2 observations (I[end / 2], src/robustPCA.jl:353)");
     return rpca_ga_dev(h, X, d, N, r, q0, tol, iters, Q, iters_done, mu_kind, mu_p);
 }
@@ -1856,7 +1856,7 @@ int tlsq_rpca_ga_mu_f64(tlsq_handle* h, const double* X, int64_t d, int64_t N, i
     CKR(use_device(h));
     if (!X || !q0 || !Q || d < 1 || N < 1 || r < 1) return set_err(TLSQ_ERR_ARG, "rpca_ga: bad arguments");
     if (mu_kind < 0 || mu_kind > 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: mu_kind must be 0 (mean), 1 (trimmed mean) or 2 (median)");
-    if (mu_kind && N > 1024) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most 1024 observations");
+    if (mu_kind && N > kGaRobustMaxN) return set_err(TLSQ_ERR_UNSUPPORTED, "rpca_ga: robust averages support at most %d observations", kGaRobustMaxN);
     if (mu_kind == 2 && N < 2) return set_err(TLSQ_ERR_ARG, "rpca_ga: entrywise_median needs at least 2 observations (I[end / 2], src/robustPCA.jl:353)");
     cudaStream_t st = h->stream;
     DevBuf bX, bq0, bQ;

@@ -47,14 +47,49 @@ function handle()
     HANDLE[]
 end
 
-_only_f64(x, name) = eltype(x) === Float64 ||
-    throw(ArgumentError("$name: only Float64 is accelerated by TotalLeastSquaresB200 (got $(eltype(x))); no CPU fallback"))
+# Element types: Float64 is native; Float32 (and integer) inputs are promoted to Float64 on the way in and the results
+# converted back, so the return types match the reference's; complex inputs are not accelerated (no CPU fallback).
+_check_eltype(x, name) = (eltype(x) <: Union{AbstractFloat, Integer}) ||
+    throw(ArgumentError("$name: element type $(eltype(x)) is not accelerated by TotalLeastSquaresB200 (real element types only); no CPU fallback"))
+_outT(x) = eltype(x) <: AbstractFloat ? eltype(x) : Float64
+_back(::Type{Float64}, a) = a
+_back(::Type{T}, a) where {T} = T.(a)
+
+# ---- plugin callables (svd / opnorm kwargs, src/robustPCA.jl:168-169): the callable travels through the `user` pointer,
+# the trampolines below are plain C function pointers (tlsq_svd_fn / tlsq_opnorm_fn of include/tlsq_b200.h) -------------
+function _svd_tramp(user::Ptr{Cvoid}, Zp::Ptr{Float64}, M::Int64, N::Int64, sv::Int64,
+                    Up::Ptr{Float64}, Sp::Ptr{Float64}, Vtp::Ptr{Float64})::Int64
+    try
+        f = unsafe_pointer_to_objref(user)::Base.RefValue{Any}
+        s = f[][1](copy(unsafe_wrap(Array, Zp, (M, N))), Int(sv))          # svd(Z, sv)   :196
+        r = min(length(s.S), M, N)
+        copyto!(unsafe_wrap(Array, Up, (M, r)), @view s.U[:, 1:r])
+        copyto!(unsafe_wrap(Array, Sp, (r,)), @view s.S[1:r])
+        copyto!(unsafe_wrap(Array, Vtp, (r, N)), @view s.Vt[1:r, :])
+        return Int64(r)
+    catch err
+        @error "svd callable failed" exception = err
+        return Int64(-1)
+    end
+end
+function _opnorm_tramp(user::Ptr{Cvoid}, Zp::Ptr{Float64}, M::Int64, N::Int64)::Float64
+    try
+        f = unsafe_pointer_to_objref(user)::Base.RefValue{Any}
+        return Float64(f[][2](unsafe_wrap(Array, Zp, (M, N))))             # opnorm(Z)::RT   :177, :225
+    catch err
+        @error "opnorm callable failed" exception = err
+        return NaN
+    end
+end
+_is_default_svd(f) = f === LinearAlgebra.svd || f === LinearAlgebra.svd!
+_is_default_opnorm(f) = f === LinearAlgebra.opnorm
 
 """
     A, E, s, sv = rpca(D; λ, maxrank, iters, tol, ρ, verbose, nonnegA, nonnegE, hankel, nukeA)
 
 Same keyword list and defaults as `TotalLeastSquares.rpca` (src/robustPCA.jl:156-170); unknown keywords are swallowed
-like the reference does (`kwargs...`, :170).  Non-default `svd` / `opnorm` callables cannot cross the C ABI.
+like the reference does (`kwargs...`, :170).  Non-default `svd` / `opnorm` callables (:168-169) cross the C ABI as
+function pointers and run on the host (`tlsq_rpca_cb_f64`); the rest of the iteration stays on the GPU.
 """
 function rpca(D::AbstractMatrix{T};
               λ              = real(T)(1.0 / sqrt(maximum(size(D)))),
@@ -70,9 +105,8 @@ function rpca(D::AbstractMatrix{T};
               svd::F1        = LinearAlgebra.svd!,
               opnorm::F2     = LinearAlgebra.opnorm,
               kwargs...) where {F1 <: Function, F2 <: Function, T}
-    _only_f64(D, "rpca")
-    (svd ∈ (LinearAlgebra.svd, LinearAlgebra.svd!) && opnorm === LinearAlgebra.opnorm) ||
-        throw(ArgumentError("rpca: custom svd/opnorm callables are not supported by the B200 path (no CPU fallback)"))
+    _check_eltype(D, "rpca")
+    To = _outT(D)
     Dd = Matrix{Float64}(D)                         # dense, column-major (the reference copies too, :176)
     M, N = size(Dd)
     d = min(M, N)
@@ -84,13 +118,33 @@ function rpca(D::AbstractMatrix{T};
             (hankel ? TLSQ_HANKEL : UInt32(0)) | (nukeA ? UInt32(0) : TLSQ_NO_NUKE_A) |
             (verbose ? TLSQ_EXACT_COST : UInt32(0))
     mr = maxrank == typemax(Int) ? Int64(0) : Int64(maxrank)
-    GC.@preserve Dd A E U S Vt hist begin
-        check(ccall((:tlsq_rpca_f64, LIB), Cint,
-                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Float64, Int64, Int64, Float64, Float64, UInt32,
-                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                     Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
-                    handle(), Dd, M, N, Float64(λ), mr, Int64(iters), Float64(tol), Float64(ρ), flags,
-                    A, E, U, S, Vt, sv, its, conv, hist))
+    if _is_default_svd(svd) && _is_default_opnorm(opnorm)
+        GC.@preserve Dd A E U S Vt hist begin
+            check(ccall((:tlsq_rpca_f64, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Float64, Int64, Int64, Float64, Float64, UInt32,
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
+                        handle(), Dd, M, N, Float64(λ), mr, Int64(iters), Float64(tol), Float64(ρ), flags,
+                        A, E, U, S, Vt, sv, its, conv, hist))
+        end
+    else
+        # user callables: C function pointers + the callables themselves behind the opaque `user` pointer.  A NULL
+        # function pointer keeps the built-in device implementation of that hook.
+        box = Ref{Any}((svd, opnorm))
+        svd_c = _is_default_svd(svd) ? C_NULL :
+            @cfunction(_svd_tramp, Int64, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}))
+        opn_c = _is_default_opnorm(opnorm) ? C_NULL :
+            @cfunction(_opnorm_tramp, Float64, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64))
+        GC.@preserve Dd A E U S Vt hist box begin
+            check(ccall((:tlsq_rpca_cb_f64, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Float64, Int64, Int64, Float64, Float64, UInt32,
+                         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Ref{Int64}, Ref{Int64}, Ref{Int32}, Ptr{Float64}),
+                        handle(), Dd, M, N, Float64(λ), mr, Int64(iters), Float64(tol), Float64(ρ), flags,
+                        svd_c, opn_c, pointer_from_objref(box),
+                        A, E, U, S, Vt, sv, its, conv, hist))
+        end
     end
     if verbose                                                        # :226, :229
         for k in 1:its[]
@@ -99,7 +153,7 @@ function rpca(D::AbstractMatrix{T};
         conv[] != 0 && println("converged")
     end
     conv[] == 0 && @warn "Maximum number of iterations reached, cost: $(abs(hist[3, max(its[], 1)])), tol: $tol"   # :232
-    A, E, LinearAlgebra.SVD(U, S, Vt), Int(sv[])
+    _back(To, A), _back(To, E), LinearAlgebra.SVD(_back(To, U), _back(To, S), _back(To, Vt)), Int(sv[])
 end
 
 """
@@ -121,11 +175,15 @@ formed on the GPU).  `μ` may be `nothing` (the default weighted mean `μ!`), `e
 """
 function rpca_ga(X::AbstractMatrix{T}, r = minimum(size(X)), U = nothing; verbose = false, tol = 1e-7,
                  iters::Int = 1000, μ = nothing, kwargs...) where T
-    _only_f64(X, "rpca_ga")
-    kind, P = μ === nothing ? (0, 0.1) :
-              μ === entrywise_trimmed_mean ? (1, 0.1) :
-              μ === entrywise_median ? (2, 0.1) :
-              (μ isa Tuple && μ[1] === entrywise_trimmed_mean) ? (1, Float64(μ[2])) :
+    _check_eltype(X, "rpca_ga")
+    To = _outT(X)
+    # the averages are recognised by NAME, so the reference's own function objects (TotalLeastSquares.μ!,
+    # TotalLeastSquares.entrywise_trimmed_mean, ...) select the device kernels just like the tags of this module
+    fname(f) = f isa Function ? nameof(f) : :_
+    kind, P = (μ === nothing || fname(μ) === :μ!) ? (0, 0.1) :
+              fname(μ) === :entrywise_trimmed_mean ? (1, 0.1) :
+              fname(μ) === :entrywise_median ? (2, 0.1) :
+              (μ isa Tuple && fname(μ[1]) === :entrywise_trimmed_mean) ? (1, Float64(μ[2])) :
               throw(ArgumentError("rpca_ga: only μ!, entrywise_trimmed_mean and entrywise_median are supported by the B200 path"))
     Xd = Matrix{Float64}(X)
     d, N = size(Xd)
@@ -141,9 +199,9 @@ function rpca_ga(X::AbstractMatrix{T}, r = minimum(size(X)), U = nothing; verbos
                      Ptr{Float64}, Ptr{Int64}),
                     handle(), Xd, d, N, Int64(r), q0, Float64(tol), Int64(iters), Cint(kind), P, Q, its))
     end
-    verbose && foreach(i -> @info("Component $i converged after $(its[i]) iterations"), 1:r)
+    verbose && foreach(i -> @info("Converged after $(its[i]) iterations"), 1:r)       # :299 (the per-iteration change of :297 stays on the device)
     any(>=(iters), its) && @warn "Reached maximum number of iterations"   # :303
-    Q
+    _back(To, Q)
 end
 
 """
@@ -154,13 +212,23 @@ an implicit (never materialised) Hankel embedding; channels and the `sv > 0` pla
 the trajectory matrix on the device.
 """
 function lowrankfilter(y::AbstractVecOrMat{T}, n = min(size(y, 1) ÷ 20, 2000); sv = 0, lag = 1, tol = 1e-3,
-                       svd = LinearAlgebra.svd!, λ = nothing, maxrank = typemax(Int), iters::Int = 1000, ρ = 1.5,
-                       verbose::Bool = false, nonnegA::Bool = false, nonnegE::Bool = false, hankel::Bool = false,
-                       nukeA = true, kwargs...) where T
-    _only_f64(y, "lowrankfilter")
+                       svd = LinearAlgebra.svd!, opnorm = LinearAlgebra.opnorm, λ = nothing, maxrank = typemax(Int),
+                       iters::Int = 1000, ρ = 1.5, verbose::Bool = false, nonnegA::Bool = false, nonnegE::Bool = false,
+                       hankel::Bool = false, nukeA = true, kwargs...) where T
+    _check_eltype(y, "lowrankfilter")
+    To = _outT(y)
     N, D = size(y, 1), size(y, 2)
     n <= N / 2 || throw(AssertionError("L has to be less than N/2 = $(N/2)"))       # :79
     lag <= n || throw(AssertionError("lag must be <= L"))                            # :80
+    if sv <= 0 && !(_is_default_svd(svd) && _is_default_opnorm(opnorm))
+        # plugin callables (test/runtests.jl:384-398): the reference's own composition (:120-127) on the materialised
+        # trajectory matrix -- the callables need the whole matrix on the host anyway
+        H = TotalLeastSquaresB200.hankel(Array{Float64}(y), n, lag)
+        A = rpca(H; tol = tol, svd = svd, opnorm = opnorm, λ = (λ === nothing ? 1 / sqrt(maximum(size(H))) : λ),
+                 maxrank = maxrank, iters = iters, ρ = ρ, verbose = verbose, nonnegA = nonnegA, nonnegE = nonnegE,
+                 hankel = hankel, nukeA = nukeA)[1]
+        return _back(To, unhankel(A, lag, N, D))
+    end
     yd = Array{Float64}(y)
     yf = similar(yd)
     svo, its, conv = Ref{Int64}(0), Ref{Int64}(0), Ref{Int32}(0)
@@ -175,7 +243,7 @@ function lowrankfilter(y::AbstractVecOrMat{T}, n = min(size(y, 1) ÷ 20, 2000); 
                     Int64(iters), Float64(tol), Float64(ρ), flags, yf, svo, its, conv, C_NULL))
     end
     conv[] == 0 && @warn "Maximum number of iterations reached, tol: $tol"
-    yf
+    _back(To, yf)
 end
 
 """
