@@ -472,6 +472,155 @@ jacobi_global_loop_kernel(int n, int np, double tol, int max_sweeps, double* __r
     if (gw == 0 && lane == 0) info[0] = sweep;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cooperative-grid form of the hierarchical tournament for 256 < n <= 512: the columns no longer fit one cluster's
+// shared memory (4 MB for X and V), so every CTA keeps its two half-blocks of `spc` columns in shared memory, rotates
+// all their pairs there (__syncthreads only), and the half-blocks move one circle-method position through a
+// double-buffered staging area in global memory (L2) with ONE grid barrier per outer round: 2C-1 = 63 grid barriers per
+// sweep at n = 512 instead of the 511 of jacobi_global_kernel (which also went to L2 for every single rotation).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(256)
+jacobi_coop_block_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n, int spc, double tol,
+                         int max_sweeps, double* __restrict__ XoA, double* __restrict__ VoA, double* __restrict__ XoB,
+                         double* __restrict__ VoB, int* __restrict__ info, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;      // fast path succeeded: nothing to do (uniform over the grid)
+    constexpr int LEN = 32 * E;
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int C = (int)gridDim.x;
+    const int c = (int)blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot_doubles = 2 * LEN;               // [X part | V part]
+    double* cur = smem;                             // slots 0..spc-1 = top half-block, spc..2spc-1 = bottom
+    int* counters = info + 2;
+
+    for (int sl = warp; sl < 2 * spc; sl += 8) {    // initial load: column j -> CTA j / (2 spc), slot j % (2 spc)
+        const int j = c * 2 * spc + sl;
+        double* dst = cur + sl * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane + 32 * e;
+            double xv = 0.0, vv = 0.0;
+            if (j < n && i < n) {
+                xv = X0[(int64_t)j * n + i];
+                vv = V0 ? V0[(int64_t)j * n + i] : (i == j ? 1.0 : 0.0);
+            }
+            dst[i] = xv;
+            dst[LEN + i] = vv;
+        }
+    }
+    __syncthreads();
+
+    auto rotate_slots = [&](int sa, int sb) -> bool {
+        double xp[E], xq[E], vp[E], vq[E];
+        double* pa = cur + sa * slot_doubles;
+        double* pb = cur + sb * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            xp[e] = pa[lane + 32 * e];
+            vp[e] = pa[LEN + lane + 32 * e];
+            xq[e] = pb[lane + 32 * e];
+            vq[e] = pb[LEN + lane + 32 * e];
+        }
+        if (!jacobi_rotate<E>(xp, xq, vp, vq, tol)) return false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            pa[lane + 32 * e] = xp[e];
+            pa[LEN + lane + 32 * e] = vp[e];
+            pb[lane + 32 * e] = xq[e];
+            pb[LEN + lane + 32 * e] = vq[e];
+        }
+        return true;
+    };
+
+    const int spe = spc + (spc & 1);                // even size of the in-block tournament
+    const int outer = 2 * C - 1;
+    int sweep = 0, stage = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        bool rotated = false;
+        for (int orow = 0; orow < outer; ++orow) {
+            if (orow == 0 && spc > 1) {
+                for (int r = 0; r < spe - 1; ++r) {         // pairs inside the two half-blocks
+                    const int half = warp / (spe / 2), pi = warp % (spe / 2);
+                    if (half < 2) {
+                        int p, q;
+                        if (pi == 0) { p = spe - 1; q = r; }
+                        else { p = (r + pi) % (spe - 1); q = (r - pi + (spe - 1)) % (spe - 1); }
+                        if (p < spc && q < spc) rotated |= rotate_slots(half * spc + p, half * spc + q);
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int r = 0; r < spc; ++r) {                 // all cross pairs of the two half-blocks
+                if (warp < spc) rotated |= rotate_slots(warp, spc + (warp + r) % spc);
+                __syncthreads();
+            }
+            if (C == 1) continue;
+            // move the half-blocks one circle-method position through the staging area (ping-pong: a CTA that is still
+            // reading round r never sees the writes of round r+1)
+            double* Xs = stage ? XoB : XoA;
+            double* Vs = stage ? VoB : VoA;
+            for (int sl = warp; sl < 2 * spc; sl += 8) {
+                const int top = sl < spc ? 1 : 0, l = top ? sl : sl - spc;
+                int dc, dtop;
+                if (top) {
+                    if (c == 0) { dc = 0; dtop = 1; }
+                    else if (c == C - 1) { dc = C - 1; dtop = 0; }
+                    else { dc = c + 1; dtop = 1; }
+                } else {
+                    if (c == 0) { dc = 1; dtop = 1; }
+                    else { dc = c - 1; dtop = 0; }
+                }
+                const double* src = cur + sl * slot_doubles;
+                const int64_t g = (int64_t)(dc * 2 * spc + (dtop ? 0 : spc) + l) * LEN;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    __stcg(Xs + g + lane + 32 * e, src[lane + 32 * e]);
+                    __stcg(Vs + g + lane + 32 * e, src[LEN + lane + 32 * e]);
+                }
+            }
+            grid.sync();
+            for (int sl = warp; sl < 2 * spc; sl += 8) {
+                const int64_t g = (int64_t)(c * 2 * spc + sl) * LEN;
+                double* dst = cur + sl * slot_doubles;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    dst[lane + 32 * e] = __ldcg(Xs + g + lane + 32 * e);
+                    dst[LEN + lane + 32 * e] = __ldcg(Vs + g + lane + 32 * e);
+                }
+            }
+            __syncthreads();
+            stage ^= 1;
+        }
+        if (rotated && lane == 0) atomicAdd(counters + sweep, 1);
+        grid.sync();
+        const int cnt = *((volatile int*)(counters + sweep));
+        if (cnt == 0) { ++sweep; break; }
+    }
+    grid.sync();      // nobody still reads the staging area: the result goes to buffer A with n-row columns
+    for (int sl = warp; sl < 2 * spc; sl += 8) {
+        const int j = c * 2 * spc + sl;
+        const double* src = cur + sl * slot_doubles;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = lane + 32 * e;
+            if (i < n) {
+                XoA[(int64_t)j * n + i] = src[i];
+                VoA[(int64_t)j * n + i] = src[LEN + i];
+            }
+        }
+    }
+    if (c == 0 && threadIdx.x == 0) info[0] = sweep;
+}
+
+// counters / sweep count of the cooperative engines
+__global__ void jacobi_info_reset_kernel(int* __restrict__ info, const int* __restrict__ run_flag) {
+    if (run_flag && run_flag[1] == 0) return;
+    if (threadIdx.x < 66) info[threadIdx.x] = 0;
+}
+
 // prepare Xo/Vo for the global engine: Xo = X0 (or G), Vo = V0 (or I)
 __global__ void jacobi_global_init_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n,
                                           double* __restrict__ Xo, double* __restrict__ Vo, int* __restrict__ info,
@@ -678,7 +827,9 @@ cudaError_t launch_global(int n, int np, double tol, int max_sweeps, double* Xo,
 size_t eig_work_doubles(int n) {
     const size_t np = (size_t)n + 34;          // padded column count upper bound
     // X0 (n*n) + Xo (np*n) + Vo (np*n) + lam_raw (np) + perm (n ints -> n doubles) + info (66 ints -> 64 doubles)
-    return (size_t)n * n + 2 * np * n + np + n + 64 + 16;
+    // 256 < n <= 512: + four staging buffers of np slots x 512 doubles for the cooperative block tournament
+    const size_t stagew = (n > 256 && n <= 512) ? 4 * ((size_t)n + 64) * 512 : 0;       // up to n + 63 padded columns
+    return (size_t)n * n + 2 * np * n + np + n + 64 + 16 + stagew;
 }
 
 cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, double* lam, double* Vs,
@@ -708,6 +859,35 @@ cudaError_t launch_eigh(const double* G, int n, const double* V0, EigWork w, dou
         else e = launch_cluster<8>(X0, V0, n, C, spc, tol, max_sweeps, w.Xo, w.Vo, w.info, run_flag, st);
         if (e != cudaSuccess) return e;
         if (launches) *launches += 1;
+    } else if (n <= 512 && getenv("TLSQ_JACOBI_GLOBAL") == nullptr) {
+        // cooperative block tournament: C CTAs x 2 half-blocks of spc columns, C * 2 * spc >= n, spc <= 8
+        const int mneed = (n + 1) / 2;
+        int C = 16;
+        while ((mneed + C - 1) / C > 8) C *= 2;
+        if (C > sm_count) C = sm_count;
+        const int spc = (mneed + C - 1) / C;
+        ncols = 2 * C * spc;
+        constexpr int LEN = 512;
+        const size_t smem = (size_t)2 * spc * 2 * LEN * sizeof(double);
+        auto kern = jacobi_coop_block_kernel<16>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        jacobi_info_reset_kernel<<<1, 96, 0, st>>>(w.info, run_flag);
+        // staging buffers live behind the regular work area (eig_work_doubles)
+        const size_t nps = (size_t)n + 64;
+        double* stg = reinterpret_cast<double*>(w.info) + 64 + 16;
+        double* XoA = stg, *VoA = stg + nps * LEN, *XoB = stg + 2 * nps * LEN, *VoB = stg + 3 * nps * LEN;
+        double tolv = tol;
+        int ms = max_sweeps, nn = n, sp = spc;
+        void* args[] = {&X0, &V0, &nn, &sp, &tolv, &ms, &XoA, &VoA, &XoB, &VoB, &w.info, &run_flag};
+        if ((e = cudaLaunchCooperativeKernel((void*)kern, dim3(C), dim3(256), args, smem, st)) != cudaSuccess) return e;
+        if (launches) *launches += 2;
+        // eig_post / permute read n-row columns from XoA / VoA
+        eig_post_kernel<<<1, 256, 2 * ncols * sizeof(double), st>>>(XoA, VoA, n, ncols, w.lam_raw, lam, w.perm, run_flag,
+                                                                     svd_mode);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        permute_cols_kernel<<<n, 128, 0, st>>>(VoA, w.perm, n, Vs, run_flag);
+        if (launches) *launches += 2;
+        return cudaGetLastError();
     } else {
         const int np = (n + 1) & ~1;
         ncols = n;
