@@ -487,8 +487,9 @@ def run_b200(args, w, rank, world, local_rank):
                                 "traffic_unit": "GB per launch (dram read+write, ncu --set full, profiles/traffic.json)",
                                 "avg_launch_ms": t_gram * 1e3}
             t_epi = e_ms / max(e_n, 1) * 1e-3
-            moved = measured_traffic("alm_stream_kernel", m, N)
-            line["roofline_epilogue"] = {"kernel": "alm_stream_kernel<PH=1> + <PH=2> (T projection, element-wise pass)",
+            moved = measured_traffic("epilogue_tma", m, N)
+            line["roofline_epilogue"] = {"kernel": "tproj_tma_kernel + alm_ew_tma_kernel (T projection, element-wise pass; "
+                                                   "TMA-staged)",
                                          "bound": "hbm", "traffic": moved,
                                          "achieved": 6 * S / t_epi * 1e-9 if t_epi > 0 else 0.0, "peak": hbm,
                                          "unit": "GB/s", "frac": (6 * S / t_epi * 1e-9) / hbm if t_epi > 0 else 0.0,
@@ -511,10 +512,13 @@ def run_b200(args, w, rank, world, local_rank):
         s_ms, s_n = prof["ga_sweep"]
         t_sw = s_ms / max(s_n, 1) * 1e-3
         bytes_ = m * N * 8
-        line["roofline"] = {"kernel": "ga_sweep_kernel<GA_PASS>", "bound": "hbm",
+        line["roofline"] = {"kernel": "ga_sweep_tma_kernel<GA_PASS>", "bound": "hbm",
                             "achieved": bytes_ / t_sw * 1e-9 if t_sw > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                             "frac": (bytes_ / t_sw * 1e-9) / hbm if t_sw > 0 else 0.0,
-                            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "traffic": None,
+                            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src}); a read-only stream can exceed "
+                                           "the copy figure (7.2 TB/s read-only, profiles/r01_microbench_fp64_hbm.log)",
+                            "traffic": measured_traffic("ga_sweep_tma_kernel", m, N),
+                            "traffic_unit": "GB per launch (dram read+write, ncu --set full, profiles/traffic.json)",
                             "avg_launch_ms": t_sw * 1e3}
     # CPU baseline beside it (rank 0, N == 1 only), bounded sample
     if world == 1 and not args.no_cpu:

@@ -12,14 +12,6 @@ timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 > ${O}_bench_c2_n
 timeout 600 python bench.py --workload c3 --steps 5 --warmup 3 > ${O}_bench_c3_n1.json 2> ${O}_bench_c3_n1.err; echo "c3 rc=$?"
 timeout 900 python bench.py --workload c5 --steps 2 --warmup 1 > ${O}_bench_c5_n1.json 2> ${O}_bench_c5_n1.err; echo "c5 rc=$?"
 TLSQ_TRACE=1 TLSQ_DEBUG_EIG=1 timeout 300 python tools/prof_driver.py c4 2 2>&1 | grep -E "tlsq" | tail -62 > ${O}_trace_c4.log
-NCU="ncu --clock-control none"
-timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file ${O}_launches_c4.csv python tools/prof_driver.py c4 1 > /dev/null 2>&1
-timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file ${O}_launches_c3.csv python tools/prof_driver.py ga 1 > /dev/null 2>&1
-FULL="$NCU --set full --import-source on -f"
-timeout 300 $FULL -k regex:'syrk_tma_kernel|tproj_tma_kernel|alm_ew_tma_kernel' --launch-skip 40 --launch-count 3 -o ${O}_ncu_c4_hot python tools/prof_driver.py c4 1 > /dev/null 2>&1
-timeout 300 $FULL -k regex:alm_fused_kernel --launch-skip 14 --launch-count 1 -o ${O}_ncu_fused python tools/prof_driver.py c4fused 1 > /dev/null 2>&1
-timeout 300 $FULL -k regex:'ga_sweep_tma_kernel' --launch-skip 6 --launch-count 2 -o ${O}_ncu_ga python tools/prof_driver.py ga 1 > /dev/null 2>&1
-timeout 400 $FULL -k regex:'jacobi_cluster_block_kernel|chol_upper_kernel|gemm_xb_kernel|si_jacobi_kernel' --launch-skip 60 -o ${O}_ncu_small python tools/prof_driver.py c4 1 > /dev/null 2>&1
 python - <<'PY'
 import json
 for f in ("bench_c4_n1", "ref_c4", "bench_c2_n1", "bench_c3_n1", "bench_c5_n1"):
