@@ -137,8 +137,6 @@ tproj_tma_kernel(const __grid_constant__ CUtensorMap mW, const EpiArgs a, int sv
         for (int p = 0; p < PR; ++p)
 #pragma unroll
             for (int u = 0; u < TC1; ++u) w[p][u] = stage_at<TC1>(stage + s * STG, tid + p * TT, u);
-        __syncthreads();                                       // the boxes are in registers: the stage can be refilled
-        if (tid == 0 && q + nstage < total) issue(q + nstage, s);
 #pragma unroll
         for (int u = 0; u < TC1; ++u) {
             const double* v = Vsm + (ch * TC1 + u) * RP;
@@ -163,6 +161,12 @@ tproj_tma_kernel(const __grid_constant__ CUtensorMap mW, const EpiArgs a, int sv
                 }
             }
         }
+        // Refill the stage only AFTER every value read from it has been consumed by an FMA: a shared-memory load that is
+        // still in flight when its thread reaches the barrier is not ordered against the TMA (async-proxy) write that
+        // thread 0 issues behind the barrier -- refilling right after the register copy produced sporadic stale / early
+        // data (non-deterministic results, caught by the repeat test in tests/test_gpu_scale.py).
+        __syncthreads();
+        if (tid == 0 && q + nstage < total) issue(q + nstage, s);
         if (++s == nstage) { s = 0; phase ^= 1u; }
     }
 }
@@ -244,8 +248,6 @@ alm_ew_tma_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant_
             if (!HANKEL) dv[u] = stage_at<TC2>(st, tid, u);
             yv[u] = stage_at<TC2>(st + HALF, tid, u);
         }
-        __syncthreads();                                       // the boxes are in registers: the stage can be refilled
-        if (tid == 0 && q + nstage < total) issue(q + nstage, s);
         double yn[TC2], w2[TC2], zv[TC2], ev[TC2];
 #pragma unroll
         for (int u = 0; u < TC2; ++u) {
@@ -275,6 +277,9 @@ alm_ew_tma_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant_
                 if (a.Zout) a.Zout[off] = zv[u];
             }
         }
+        // refill only after the values read from the stage have been consumed (see tproj_tma_kernel)
+        __syncthreads();
+        if (tid == 0 && q + nstage < total) issue(q + nstage, s);
         if (++s == nstage) { s = 0; phase ^= 1u; }
         if (++ch == nch) { ch = 0; ++tile; }
     }
