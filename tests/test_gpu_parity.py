@@ -99,10 +99,10 @@ def test_golden_vectors():
 ])
 def test_rpca_parity_fixed_iterations(M, N, r, kw, its, monkeypatch):
     D = T.synth.lowrank_sparse_np(M, N, r, 0.05, seed=M + N, nonneg=bool(kw.get("nonnegA")))
-    # n = 256 has three interchangeable per-iteration pipelines (solver.cu picks by memory): cover all of them
+    # n = 256: two-kernel pipeline (TMA-staged and register-prefetch streaming kernels) and the one-pass kernel
     pipelines = [{}]
     if N == 256 and M >= 4096:
-        pipelines = [{"TLSQ_FUSED": "0"}, {"TLSQ_FUSED": "1"}, {"TLSQ_FUSED": "1", "TLSQ_FUSED_WS": "1"}]
+        pipelines = [{"TLSQ_FUSED": "0"}, {"TLSQ_FUSED": "1"}, {"TLSQ_FUSED": "0", "TLSQ_STREAM_TMA": "0"}]
     ref = None
     for env in pipelines:
         for k_, v_ in env.items():
@@ -284,10 +284,6 @@ def test_fused_pipeline_equals_two_kernel_pipeline(monkeypatch):
     yf2, info2 = T.lowrankfilter(yn, 256, return_info=True)
     monkeypatch.delenv("TLSQ_INPLACE_Y")
     assert relF(yf2, yo) < TOL and info2["iters"] == info["iters"]
-    monkeypatch.setenv("TLSQ_FUSED_WS", "1")                              # warp-specialised variant of the kernel
-    yf4, info4 = T.lowrankfilter(yn, 256, return_info=True)
-    monkeypatch.delenv("TLSQ_FUSED_WS")
-    assert relF(yf4, yo) < TOL and info4["iters"] == info["iters"]
     monkeypatch.delenv("TLSQ_FUSED")
     yf3 = T.lowrankfilter(yn[:-1], 256)                                   # odd row count: two-kernel pipeline
     assert relF(yf3, O.lowrankfilter(yn[:-1], 256)) < TOL

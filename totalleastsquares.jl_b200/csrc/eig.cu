@@ -7,12 +7,15 @@
 // columns of X are mutually orthogonal; then X = V * Lambda.  Warm start: V0 = eigenvectors of the previous ALM
 // iteration, X0 = G * V0 is already nearly orthogonal, so 1-3 sweeps suffice instead of 6-10.
 //
-// Two engines:
-//  * jacobi_cluster_kernel (n <= 256): ONE thread-block cluster of up to 16 CTAs holds all columns (X and V parts,
-//    double buffered) in distributed shared memory.  One warp per column pair; the round-robin tournament moves
-//    every column one seat per round, written straight into the destination CTA's shared memory (DSMEM stores),
-//    one cluster barrier per round.  Dot products use warp-shuffle reductions; rotations happen in registers.
-//  * jacobi_global_kernel (any n <= 512): cooperative grid, columns stay in L2, grid barrier per round.
+// Engines:
+//  * jacobi_cluster_block_kernel (n <= 256): ONE thread-block cluster of up to 16 CTAs holds all columns (X and V parts)
+//    in distributed shared memory; hierarchical tournament: every CTA rotates the cross pairs of its two half-blocks in
+//    place, then the half-blocks move one circle-method position through DSMEM (one cluster barrier per outer round).
+//  * jacobi_coop_block_kernel (256 < n <= 512): the same tournament on a cooperative grid, half-blocks in shared memory,
+//    exchange through a double-buffered staging area in L2 (one grid barrier per outer round).
+//  * jacobi_global_kernel / jacobi_global_loop_kernel (fallback / n > 512): cooperative grid, columns stay in L2.
+// svd mode: the same kernels orthogonalise the columns of a GENERAL square matrix K (K V = U S) -- used by the
+// CholeskyQR2-style refinement of the returned SVD (solver.cu); chol_upper_kernel is the Cholesky factor it needs.
 #include <cooperative_groups.h>
 #include "kernels.h"
 
@@ -91,133 +94,7 @@ __device__ __forceinline__ bool jacobi_rotate(double (&xp)[E], double (&xq)[E], 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Cluster engine.  m = C * spc seats, seat s holds the pair (top[s], bot[s]); CTA c owns seats
-// [c*spc, (c+1)*spc).  Slot layout per buffer: slot (2*ls + which) * 2*LEN doubles = [X part | V part].
-// Tournament step (circle method): top[0] fixed; top[s] -> top[s+1] (1 <= s <= m-2); top[m-1] -> bot[m-1];
-// bot[s] -> bot[s-1] (s >= 1); bot[0] -> top[1].  (m == 1: nothing moves.)
-// ---------------------------------------------------------------------------------------------------
-template <int E>
-__global__ void __launch_bounds__(256)
-jacobi_cluster_kernel(const double* __restrict__ X0, const double* __restrict__ V0, int n, int spc,
-                      double tol, int max_sweeps, double* __restrict__ Xo, double* __restrict__ Vo,
-                      int* __restrict__ info, const int* __restrict__ run_flag) {
-    if (run_flag && run_flag[1] == 0) return;      // fast path succeeded: nothing to do (uniform over the cluster)
-    constexpr int LEN = 32 * E;
-    extern __shared__ double smem[];
-    __shared__ int counters[64];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int c = (int)cluster.block_rank();
-    const int m = C * spc;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot_doubles = 2 * LEN;
-    const int buf_doubles = 2 * spc * slot_doubles;
-    double* buf0 = smem;
-    double* buf1 = smem + buf_doubles;
-
-    if (threadIdx.x < 64) counters[threadIdx.x] = 0;
-
-    // initial load: column j -> seat j/2, top if j even else bot.  Columns >= n are zero dummies.
-    for (int w = warp; w < 2 * spc; w += 8) {
-        const int ls = w >> 1, which = w & 1;
-        const int j = 2 * (c * spc + ls) + which;
-        double* dst = buf0 + (2 * ls + which) * slot_doubles;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int i = lane + 32 * e;
-            double xv = 0.0, vv = 0.0;
-            if (j < n && i < n) {
-                xv = X0[(int64_t)j * n + i];
-                vv = V0 ? V0[(int64_t)j * n + i] : (i == j ? 1.0 : 0.0);
-            }
-            dst[i] = xv;
-            dst[LEN + i] = vv;
-        }
-    }
-    cluster.sync();
-
-    int* counters0 = cluster.map_shared_rank(counters, 0);
-    double* cur = buf0;
-    double* nxt = buf1;
-    int sweep = 0;
-    const int rounds = 2 * m - 1;
-    for (; sweep < max_sweeps; ++sweep) {
-        bool rotated = false;
-        for (int round = 0; round < rounds; ++round) {
-            if (warp < spc) {
-                const int ls = warp;
-                const int s = c * spc + ls;
-                double xp[E], xq[E], vp[E], vq[E];
-                const double* pt = cur + (2 * ls) * slot_doubles;
-                const double* pb = cur + (2 * ls + 1) * slot_doubles;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    xp[e] = pt[lane + 32 * e];
-                    vp[e] = pt[LEN + lane + 32 * e];
-                    xq[e] = pb[lane + 32 * e];
-                    vq[e] = pb[LEN + lane + 32 * e];
-                }
-                rotated |= jacobi_rotate<E>(xp, xq, vp, vq, tol);
-                // destinations
-                int ts, tw, bs, bw;            // seat / which for the top and bottom column
-                if (m == 1) { ts = 0; tw = 0; bs = 0; bw = 1; }
-                else {
-                    if (s == 0) { ts = 0; tw = 0; }
-                    else if (s == m - 1) { ts = m - 1; tw = 1; }
-                    else { ts = s + 1; tw = 0; }
-                    if (s == 0) { bs = 1; bw = 0; }
-                    else { bs = s - 1; bw = 1; }
-                }
-                {
-                    const int dc = ts / spc, dl = ts - dc * spc;
-                    double* base = (dc == c) ? nxt : cluster.map_shared_rank(nxt, dc);
-                    double* dst = base + (2 * dl + tw) * slot_doubles;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        dst[lane + 32 * e] = xp[e];
-                        dst[LEN + lane + 32 * e] = vp[e];
-                    }
-                }
-                {
-                    const int dc = bs / spc, dl = bs - dc * spc;
-                    double* base = (dc == c) ? nxt : cluster.map_shared_rank(nxt, dc);
-                    double* dst = base + (2 * dl + bw) * slot_doubles;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        dst[lane + 32 * e] = xq[e];
-                        dst[LEN + lane + 32 * e] = vq[e];
-                    }
-                }
-            }
-            cluster.sync();
-            double* tmp = cur; cur = nxt; nxt = tmp;
-        }
-        if (rotated && lane == 0) atomicAdd(counters0 + sweep, 1);
-        cluster.sync();
-        const int cnt = *((volatile int*)(counters0 + sweep));
-        if (cnt == 0) { ++sweep; break; }
-    }
-    cluster.sync();   // nobody may exit while a peer still reads counters0 / writes DSMEM
-
-    // write back: column index = 2*seat + which (order is irrelevant; eig_post sorts)
-    for (int w = warp; w < 2 * spc; w += 8) {
-        const int ls = w >> 1, which = w & 1;
-        const int j = 2 * (c * spc + ls) + which;
-        const double* src = cur + (2 * ls + which) * slot_doubles;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int i = lane + 32 * e;
-            if (i < n) {
-                Xo[(int64_t)j * n + i] = src[i];
-                Vo[(int64_t)j * n + i] = src[LEN + i];
-            }
-        }
-    }
-    if (c == 0 && threadIdx.x == 0) info[0] = sweep;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Cluster engine, hierarchical tournament (default).  Every CTA holds two HALF-BLOCKS of spc columns (top / bottom).
+// Cluster engine, hierarchical tournament (the flat one-barrier-per-round tournament of round 1 was 5.8 ms vs 4.2 ms).  Every CTA holds two HALF-BLOCKS of spc columns (top / bottom).
 // One sweep = 2C-1 outer rounds; in an outer round a CTA rotates all spc x spc cross pairs of its two half-blocks in
 // spc inner rounds (pair (T[w], B[(w+r) % spc]) on warp w, in place in shared memory, __syncthreads between rounds),
 // then the half-blocks move one position of the circle method (top[0] fixed, top[c] -> top[c+1], top[C-1] -> bot[C-1],
@@ -787,8 +664,7 @@ cudaError_t launch_cluster(const double* X0, const double* V0, int n, int C, int
                            double* Xo, double* Vo, int* info, const int* run_flag, cudaStream_t st) {
     constexpr int LEN = 32 * E;
     const size_t smem = (size_t)2 * 2 * spc * 2 * LEN * sizeof(double);
-    static const bool flat = getenv("TLSQ_JACOBI_FLAT") != nullptr;      // comparison hook: one cluster barrier per round
-    auto kern = flat ? jacobi_cluster_kernel<E> : jacobi_cluster_block_kernel<E>;
+    auto kern = jacobi_cluster_block_kernel<E>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (C > 8) {

@@ -90,22 +90,6 @@ __device__ __forceinline__ double dot_rp(const double (&t)[RP], const double* __
     return (a0 + a1) + (a2 + a3);
 }
 
-// same with v in global memory (read-only path, L1 resident)
-template <int RP>
-__device__ __forceinline__ double dot_rp_g(const double (&t)[RP], const double* __restrict__ v) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int c = 0; c < RP; c += 4) {
-        const double2 v0 = __ldg(reinterpret_cast<const double2*>(v + c));
-        const double2 v1 = __ldg(reinterpret_cast<const double2*>(v + c + 2));
-        a0 = fma(t[c], v0.x, a0);
-        a1 = fma(t[c + 1], v0.y, a1);
-        a2 = fma(t[c + 2], v1.x, a2);
-        a3 = fma(t[c + 3], v1.y, a3);
-    }
-    return (a0 + a1) + (a2 + a3);
-}
-
 // TMA store of a shared-memory tile (bulk async group); the generic-proxy writes must be fenced by their writers
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
@@ -407,365 +391,9 @@ alm_fused_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__
 }
 
 
-// =====================================================================================================================
-// Warp-specialised variant (default): 8 MMA warps keep the FP64 tensor pipe busy with the Gram of tile t while 4
-// element-wise warps produce the operand tile t+1 (double-buffered, XOR-swizzled) -- the dependency / shared-memory
-// latencies of the element-wise chains are hidden behind DMMA issue instead of being exposed in a lock-step phase.
-// Registers are re-partitioned with setmaxnreg (MMA warps 200, element-wise warps 104).  Synchronisation is all
-// mbarrier based (local + remote arrives through DSMEM); no CTA-wide or cluster-wide barrier inside the tile loop.
-// =====================================================================================================================
-constexpr int WS_THREADS = 384;
-constexpr int W2S_DOUBLES = FN * FR;                // one swizzled operand tile: 64 KB
-constexpr int VT_LD = 16;                           // leading dimension of the packed V_{k-1}' scratch (global, L1 resident)
-
-__device__ __forceinline__ int swz(int col, int row) { return col * FR + (row ^ ((col & 3) << 2)); }
-
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void ew_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-template <int N1>
-__device__ __forceinline__ void gram_phase_ws(double (&acc)[9][4][2], const double* __restrict__ W2, int aA, int aB,
-                                              const int (&bo)[9], int x) {
-#pragma unroll 1
-    for (int ks = 0; ks < FR / 4; ++ks) {
-        const double* wk = W2 + 4 * (ks ^ x);
-        double a1[4], a2[4];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            a1[mi] = wk[aA + 8 * mi * FR];
-            if (N1 < 9) a2[mi] = wk[aB + 8 * mi * FR];
-        }
-#pragma unroll
-        for (int s = 0; s < 9; ++s) {
-            const double b = wk[bo[s]];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) dmma884(acc[s][mi][0], acc[s][mi][1], s < N1 ? a1[mi] : a2[mi], b);
-        }
-    }
-}
-
-template <int RP, bool HANKEL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1)
-alm_fused_ws_kernel(const __grid_constant__ CUtensorMap mD, const __grid_constant__ CUtensorMap mY,
-                    const __grid_constant__ CUtensorMap mTp, const __grid_constant__ CUtensorMap mTn,
-                    const __grid_constant__ CUtensorMap mYo, const __grid_constant__ CUtensorMap mTo, const FusedDev p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    double* W2 = reinterpret_cast<double*>(smem);               // [2][256][32] swizzled operand tiles
-    double* Ds = W2 + 2 * W2S_DOUBLES;                          // [128][32] own-half D tile          (TMA)
-    double* Ys = Ds + TILE_DOUBLES;                             // [128][32] own-half Y tile (TMA in, Y_k staged out)
-    double* Vks = Ys + TILE_DOUBLES;                            // [128][RP] own-half rows of V_k
-    double* Tps = Vks + FH * RP;                                // [RP][32]  T_{k-1} tile             (TMA)
-    double* Tns = Tps + RP * FR;                                // [RP][32]  T_k tile (TMA in when given, else staged out)
-    double* Tsum = Tns + RP * FR;                               // [2][RP][32] partial row sums of the two CTAs
-    double* fs = Tsum + 2 * RP * FR;                            // [RP]
-    double* red = fs + RP;                                      // [4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4);      // ld_full, w_full[2], w_empty[2], peer_empty[2], t_full
-    uint64_t* ld_full = bars;
-    uint64_t* w_full = bars + 1;
-    uint64_t* w_empty = bars + 3;
-    uint64_t* peer_empty = bars + 5;
-    uint64_t* t_full = bars + 7;
-
-    const FusedArgs& a = p.a;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
-    const int cl = blockIdx.x >> 1;
-    const int c0 = (int)rank * FH;
-    const int go = a.gram_of;
-    const bool simple = (go == FUSED_GRAM_W) || (go == FUSED_GRAM_D);
-
-    if (tid == 0) {
-        mbar_init(ld_full, 1);
-        mbar_init(&w_full[0], 8); mbar_init(&w_full[1], 8);           // 4 local + 4 remote element-wise warps
-        mbar_init(&w_empty[0], 8); mbar_init(&w_empty[1], 8);         // 8 local MMA warps
-        mbar_init(&peer_empty[0], 8); mbar_init(&peer_empty[1], 8);   // 8 remote MMA warps
-        mbar_init(t_full, 1);                                         // the peer's reducing warp
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int idx = tid; idx < FH * RP; idx += WS_THREADS) {
-        const int jl = idx % FH, c = idx / FH;
-        Vks[jl * RP + c] = (c < a.svp && a.Vs) ? __ldg(a.Vs + (int64_t)c * FN + c0 + jl) : 0.0;
-    }
-    if (tid < RP) fs[tid] = (tid < a.svp && a.fvec) ? __ldg(a.fvec + tid) : 0.0;
-    __syncthreads();
-    cluster_arrive();            // barriers initialised and the peer's shared memory live before any remote access
-    cluster_wait();
-
-    const int ntl = (p.ntiles > cl) ? (p.ntiles - cl + p.ncluster - 1) / p.ncluster : 0;    // tiles of this cluster
-
-    if (warp >= 8) {
-        // =============================== element-wise (producer) warps ==============================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        const int ew = warp - 8;
-        const int etid = tid - 256;
-        const bool nnA = a.nonnegA != 0;
-        constexpr int UB = 4;
-        const uint32_t tx_bytes = (uint32_t)((p.has_d ? TILE_BYTES : 0) + (p.has_y ? TILE_BYTES : 0) +
-                                             (p.has_tp ? RP * FR * 8 : 0) + (p.has_tn ? RP * FR * 8 : 0));
-        auto issue = [&](int tile) {
-            mbar_expect_tx(ld_full, tx_bytes);
-            if (p.has_d) tma_load_2d(Ds, &mD, tile * FR, c0, ld_full);
-            if (p.has_y) tma_load_2d(Ys, &mY, tile * FR, c0, ld_full);
-            if (p.has_tp) tma_load_2d(Tps, &mTp, tile * FR, 0, ld_full);
-            if (p.has_tn) tma_load_2d(Tns, &mTn, tile * FR, 0, ld_full);
-        };
-        if (etid == 0 && ntl > 0) issue(cl);
-        const uint32_t w2_peer = map_peer(smem_u32(W2), peer);
-        const uint32_t tsum_peer = map_peer(smem_u32(Tsum), peer);
-        const uint32_t wfull_peer = map_peer(smem_u32(w_full), peer);
-        const uint32_t tfull_peer = map_peer(smem_u32(t_full), peer);
-        const bool push = (rank == 0) || (ew < 2);    // CTA 0 needs columns 128..191 of CTA 1; CTA 1 all of CTA 0's
-        const double* vpt = a.VpT + (size_t)(c0 + 32 * ew) * VT_LD;
-        double zz = 0.0;
-
-        for (int it = 0; it < ntl; ++it) {
-            const int tile = cl + it * p.ncluster;
-            const int b = it & 1;
-            const uint32_t par = (uint32_t)((it >> 1) & 1);
-            double* W2b = W2 + b * W2S_DOUBLES;
-            const uint32_t w2b_peer = w2_peer + (uint32_t)b * (W2S_DOUBLES * 8);
-            const int64_t row = (int64_t)tile * FR + lane;
-            const bool rowok = row < a.M;
-            mbar_wait(ld_full, (uint32_t)(it & 1));
-            mbar_wait_cluster(&w_empty[b], par ^ 1u);          // our MMA warps are done with tile it-2 in this buffer
-            mbar_wait_cluster(&peer_empty[b], par ^ 1u);       // ... and so are the peer's (we push into its buffer)
-
-            if (simple) {
-                // operand = D or W_k(A_{k-1}, Y_{k-1}); nothing else to do
-                double tp[RP];
-#pragma unroll
-                for (int c = 0; c < RP; ++c) tp[c] = (p.has_tp && c < a.svp_prev) ? Tps[c * FR + lane] : 0.0;
-#pragma unroll 1
-                for (int u = 0; u < 32; ++u) {
-                    const int jl = 32 * ew + u;
-                    const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
-                    double val = d;
-                    if (go == FUSED_GRAM_W) {
-                        double ap = dot_rp_g<RP>(tp, vpt + u * VT_LD);
-                        ap = (nnA && !(__double_as_longlong(ap) > 0)) ? 0.0 : ap;
-                        double e, w;
-                        alm_ew(d, ap, Ys[jl * FR + lane], a.im, a.eps, a.nonnegE, e, w);
-                        val = w;
-                    }
-                    const int off = swz(c0 + jl, lane);
-                    W2b[off] = val;
-                    if (push) st_cluster(w2b_peer + (uint32_t)off * 8u, val);
-                }
-            } else {
-                // ---- E_k (parked in the operand slot), W_k and the partial row sums of T = W_k V_k -------------------
-                double tr[RP];
-                {
-                    double tp[RP];
-#pragma unroll
-                    for (int c = 0; c < RP; ++c) {
-                        tp[c] = (p.has_tp && c < a.svp_prev) ? Tps[c * FR + lane] : 0.0;
-                        tr[c] = 0.0;
-                    }
-#pragma unroll 1
-                    for (int u0 = 0; u0 < 32; u0 += UB) {
-                        double av[UB], wv[UB];
-#pragma unroll
-                        for (int u = 0; u < UB; ++u) av[u] = dot_rp_g<RP>(tp, vpt + (u0 + u) * VT_LD);
-#pragma unroll
-                        for (int u = 0; u < UB; ++u) {
-                            const int jl = 32 * ew + u0 + u;
-                            const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
-                            const double ap = (nnA && !(__double_as_longlong(av[u]) > 0)) ? 0.0 : av[u];
-                            double e, w;
-                            alm_ew(d, ap, Ys[jl * FR + lane], a.im, a.eps, a.nonnegE, e, w);
-                            W2b[swz(c0 + jl, lane)] = e;
-                            wv[u] = w;
-                        }
-                        if (a.compute_T) {
-#pragma unroll
-                            for (int u = 0; u < UB; ++u) {
-                                const double* v = Vks + (32 * ew + u0 + u) * RP;
-#pragma unroll
-                                for (int c = 0; c < RP; c += 2) {
-                                    const double2 vv = *reinterpret_cast<const double2*>(v + c);
-                                    tr[c] = fma(wv[u], vv.x, tr[c]);
-                                    tr[c + 1] = fma(wv[u], vv.y, tr[c + 1]);
-                                }
-                            }
-                        }
-                    }
-                }
-                double tk[RP];
-                if (a.compute_T) {
-                    // row sums over the four element-wise warps (serial accumulation in our Tsum slot), then to the peer.
-                    // The slots were last read in the previous tile's second half: by us (ordered by ew_bar) and by the
-                    // peer (its arrival on our w_full of the previous tile says it is done).
-                    if (it > 0 && ew == 3) mbar_wait_cluster(&w_full[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
-#pragma unroll 1
-                    for (int r = 0; r < 4; ++r) {
-                        if (ew == r) {
-#pragma unroll
-                            for (int c = 0; c < RP; ++c) {
-                                const int idx = (int)rank * RP * FR + c * FR + lane;
-                                const double v = (r ? Tsum[idx] : 0.0) + tr[c];
-                                Tsum[idx] = v;
-                                if (r == 3) st_cluster(tsum_peer + (uint32_t)idx * 8u, v);
-                            }
-                            if (r == 3) {
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_remote(tfull_peer);
-                            }
-                        }
-                        ew_bar();
-                    }
-                    mbar_wait_cluster(t_full, (uint32_t)(it & 1));
-#pragma unroll
-                    for (int c = 0; c < RP; ++c) {
-                        tk[c] = fs[c] * (Tsum[c * FR + lane] + Tsum[(RP + c) * FR + lane]);
-                        if (rank == 0 && (c & 3) == ew) Tns[c * FR + lane] = tk[c];        // staged for the TMA store
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < RP; ++c) tk[c] = c < a.svp ? Tns[c * FR + lane] : 0.0;
-                }
-                // ---- A_k, Z, Y_k, ||Z||^2, W_{k+1} -> operand tile of both CTAs ----------------------------------------
-#pragma unroll 1
-                for (int u0 = 0; u0 < 32; u0 += UB) {
-                    double av[UB];
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) av[u] = dot_rp<RP>(tk, Vks + (32 * ew + u0 + u) * RP);
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        const int jl = 32 * ew + u0 + u;
-                        const int off = swz(c0 + jl, lane);
-                        const double d = HANKEL ? (rowok ? __ldg(a.D.p + row + c0 + jl) : 0.0) : Ds[jl * FR + lane];
-                        const double yp = Ys[jl * FR + lane];
-                        const double e = W2b[off];
-                        const double an = (nnA && !(__double_as_longlong(av[u]) > 0)) ? 0.0 : av[u];   // max.(A, 0) :218
-                        const double z = __dsub_rn(__dsub_rn(d, an), e);                    // @. Z = D - A - E  :221
-                        const double yn = __dadd_rn(yp, __dmul_rn(a.mu, z));                // @. Y = Y + mu*Z   :222
-                        zz = fma(z, z, zz);
-                        Ys[jl * FR + lane] = yn;                                            // staged for the TMA store
-                        double e2, w2;
-                        alm_ew(d, an, yn, a.im_next, a.eps_next, a.nonnegE, e2, w2);        // SVT input of iteration k+1
-                        const double val = (go == FUSED_GRAM_WNEXT) ? w2 : z;
-                        W2b[off] = val;
-                        if (push) st_cluster(w2b_peer + (uint32_t)off * 8u, val);
-                    }
-                }
-                fence_async_smem();      // Y_k / T_k tiles were written through the generic proxy
-            }
-            // operand tile complete (our columns): tell our MMA warps and the peer's
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_local(&w_full[b]);
-                mbar_arrive_remote(wfull_peer + (uint32_t)b * 8u);
-            }
-            ew_bar();                    // every element-wise warp is done with the staging buffers
-            if (etid == 0) {
-                if (!simple) {
-                    if (a.write_Y) tma_store_2d(&mYo, tile * FR, c0, Ys);
-                    if (a.compute_T && rank == 0 && a.Tn) tma_store_2d(&mTo, tile * FR, 0, Tns);
-                    tma_commit();
-                    tma_wait_read0();
-                }
-                if (it + 1 < ntl) issue(tile + p.ncluster);
-            }
-        }
-        zz = warp_sum(zz);
-        if (lane == 0) red[ew] = zz;
-        ew_bar();
-        if (etid == 0) {
-            a.zpart[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
-            tma_wait_all0();
-        }
-    } else {
-        // =============================== MMA (consumer) warps ==========================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-        const int g = lane >> 2, t = lane & 3;
-        const int x = g & 3;                               // swizzle key of every column this lane loads: (col & 3) = g & 3
-        int bo[9];
-        int rowA, rowB, n1 = 0;
-        {
-            const uint8_t* rt = p.tab.row[rank][warp];
-            const uint8_t* ct = p.tab.cs[rank][warp];
-            rowA = rt[0];
-            rowB = rt[8];
-#pragma unroll
-            for (int s = 0; s < 9; ++s) {
-                bo[s] = (8 * (int)ct[s] + g) * FR + t;
-                n1 += ((int)rt[s] == rowA) ? 1 : 0;
-            }
-        }
-        const int aA = (32 * rowA + g) * FR + t;
-        const int aB = (32 * rowB + g) * FR + t;
-        double acc[9][4][2];
-#pragma unroll
-        for (int s = 0; s < 9; ++s)
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) acc[s][mi][0] = acc[s][mi][1] = 0.0;
-        const uint32_t pempty_peer = map_peer(smem_u32(peer_empty), peer);
-
-        for (int it = 0; it < ntl; ++it) {
-            const int b = it & 1;
-            const double* W2b = W2 + b * W2S_DOUBLES;
-            mbar_wait_cluster(&w_full[b], (uint32_t)((it >> 1) & 1));
-            switch (n1) {
-                case 1: gram_phase_ws<1>(acc, W2b, aA, aB, bo, x); break;
-                case 2: gram_phase_ws<2>(acc, W2b, aA, aB, bo, x); break;
-                case 3: gram_phase_ws<3>(acc, W2b, aA, aB, bo, x); break;
-                case 4: gram_phase_ws<4>(acc, W2b, aA, aB, bo, x); break;
-                case 5: gram_phase_ws<5>(acc, W2b, aA, aB, bo, x); break;
-                case 6: gram_phase_ws<6>(acc, W2b, aA, aB, bo, x); break;
-                case 7: gram_phase_ws<7>(acc, W2b, aA, aB, bo, x); break;
-                case 8: gram_phase_ws<8>(acc, W2b, aA, aB, bo, x); break;
-                default: gram_phase_ws<9>(acc, W2b, aA, aB, bo, x); break;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_local(&w_empty[b]);
-                mbar_arrive_remote(pempty_peer + (uint32_t)b * 8u);
-            }
-        }
-        // partial Gram of this cluster (disjoint tiles per CTA)
-        double* P = a.partial + (size_t)cl * (FN * FN);
-        const uint8_t* rt = p.tab.row[rank][warp];
-        const uint8_t* ct = p.tab.cs[rank][warp];
-#pragma unroll
-        for (int s = 0; s < 9; ++s) {
-            const int r0 = 32 * (int)rt[s] + g;
-            const int cc = 8 * (int)ct[s] + 2 * t;
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                P[(size_t)cc * FN + r0 + 8 * mi] = acc[s][mi][0];
-                P[(size_t)(cc + 1) * FN + r0 + 8 * mi] = acc[s][mi][1];
-            }
-        }
-    }
-    __syncthreads();
-    cluster_arrive();            // keep this CTA's shared memory alive until the peer is done with it
-    cluster_wait();
-}
-
-// VpT[j][c] = V_{k-1}[j, c] (c < svp_prev, else 0): row-contiguous copy read by the element-wise warps through L1
-__global__ void pack_vt_kernel(const double* __restrict__ Vp, int svp_prev, double* __restrict__ VpT) {
-    for (int idx = threadIdx.x; idx < FN * VT_LD; idx += blockDim.x) {
-        const int j = idx / VT_LD, c = idx % VT_LD;
-        VpT[idx] = (Vp && c < svp_prev) ? Vp[(size_t)c * FN + j] : 0.0;
-    }
-}
+// (A warp-specialised variant -- 8 MMA warps + 4 producer warps, setmaxnreg, mbarrier-only synchronisation -- was built and
+// measured in round 1: 8.4 ms against 5.1 ms for this lock-step kernel, because the producers' 2-cycle FP64 instructions
+// queue behind the 16-cycle DMMAs on the shared FP64 pipe.  It was removed in round 2; see DESIGN.md.)
 
 // G[i,j] = G[j,i] = sum over the clusters (fixed order) of the upper-triangular partials; zz = sum of the CTA partials
 __global__ void fused_reduce_kernel(const double* __restrict__ partial, int ncluster, const double* __restrict__ zpart,
@@ -842,22 +470,9 @@ size_t smem_bytes() {
            2 * (size_t)RP * FR * 8 + (size_t)RP * 8 + 8 * 8 + 16;
 }
 
-inline bool use_ws() {
-    // 1: warp-specialised variant (4 producer + 8 MMA warps).  Measured slower than the lock-step kernel on B200: the
-    // producers' 2-cycle FP64 instructions queue behind 16-cycle DMMAs on the shared FP64 pipe (kernels).
-    const char* e = getenv("TLSQ_FUSED_WS");
-    return e && e[0] == '1';
-}
-
 struct Inst {
     int ncluster = -1;      // co-resident clusters (queried once)
 };
-
-template <int RP>
-size_t smem_bytes_ws() {
-    return 2 * (size_t)W2S_DOUBLES * 8 + 2 * (size_t)TILE_BYTES + (size_t)FH * RP * 8 + 2 * (size_t)RP * FR * 8 +
-           2 * (size_t)RP * FR * 8 + (size_t)RP * 8 + 4 * 8 + 8 * 8 + 16;
-}
 
 template <class Kern>
 int query_clusters(Kern kern, int threads, size_t smem, int sm_count) {
@@ -880,23 +495,7 @@ template <int RP, bool HANKEL>
 cudaError_t launch_inst(const CUtensorMap& mD, const CUtensorMap& mY, const CUtensorMap& mTp, const CUtensorMap& mTn,
                         const CUtensorMap& mYo, const CUtensorMap& mTo, FusedDev p, int sm_count, cudaStream_t st,
                         int* ncluster_out) {
-    static Inst inst, inst_ws;
-    const bool ws = use_ws();
-    if (ws) {
-        auto kern = alm_fused_ws_kernel<RP, HANKEL>;
-        const size_t smem = smem_bytes_ws<RP>();
-        if (inst_ws.ncluster < 0) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            inst_ws.ncluster = query_clusters(kern, WS_THREADS, smem, sm_count);
-        }
-        int nc = inst_ws.ncluster;
-        if (nc > p.ntiles) nc = p.ntiles > 0 ? p.ntiles : 1;
-        p.ncluster = nc;
-        *ncluster_out = nc;
-        kern<<<2 * nc, WS_THREADS, smem, st>>>(mD, mY, mTp, mTn, mYo, mTo, p);
-        return cudaGetLastError();
-    }
+    static Inst inst;
     auto kern = alm_fused_kernel<RP, HANKEL>;
     const size_t smem = smem_bytes<RP>();
     if (inst.ncluster < 0) {
@@ -923,7 +522,7 @@ cudaError_t launch_rp(bool hankel, const CUtensorMap* m, const FusedDev& p, int 
 FusedStripTab fused_strip_table() { return make_tab(); }
 
 size_t fused_partial_doubles(int sm_count) {
-    return (size_t)(sm_count / 2) * FN * FN + (size_t)sm_count + 8 + (size_t)FN * VT_LD;
+    return (size_t)(sm_count / 2) * FN * FN + (size_t)sm_count + 8;
 }
 
 bool fused_eligible(const MatSrc& D, bool hankel, int64_t M, int64_t N) {
@@ -970,13 +569,7 @@ cudaError_t launch_alm_fused(const FusedArgs& a, bool hankel, const double* Yp, 
     ok &= t_out ? encode_map(&m[5], a.Tn, a.M, kStreamMaxRank, a.ldt, FR, rp) : encode_map(&m[5], any, 32, 128, 32, FR, rp);
     if (!ok) return cudaErrorInvalidValue;
     if (needs_tk && a.write_Y && !a.Yn) return cudaErrorInvalidValue;
-    // packed V_{k-1}' for the element-wise warps of the warp-specialised kernel (L1-resident read-only data)
-    double* vpt = a.zpart + (((size_t)sm_count + 8 + 1) & ~(size_t)1);
-    p.a.VpT = vpt;
-    if (use_ws()) {
-        pack_vt_kernel<<<1, 256, 0, st>>>(a.Vp, a.svp_prev, vpt);
-        if (launches) *launches += 1;
-    }
+    p.a.VpT = nullptr;
     int nc = 0;
     cudaError_t e;
     switch (rp) {
