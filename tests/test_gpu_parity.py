@@ -94,6 +94,7 @@ def test_golden_vectors():
     (10000, 128, 6, {"nonnegA": True, "nonnegE": True}, 14),
     (3000, 96, 40, {}, 10),                                  # svp > 32: fused tile epilogue, full Jacobi
     (6000, 512, 8, {}, 5),                                   # n = 512: cooperative-grid Jacobi
+    (9000, 512, 28, {}, 7),                                  # n = 512, rank 25..32: column-chunked streaming epilogue
     (300, 500, 4, {}, 8),                                    # wide: solved on the transpose
     (33, 7, 2, {}, 6), (1, 5, 1, {}, 3), (7, 1, 1, {}, 3),   # ragged / degenerate
 ])

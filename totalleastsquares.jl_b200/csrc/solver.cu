@@ -401,8 +401,10 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
         }
         return TLSQ_OK;
     };
+    // N x 32 scratch of the column-chunked streaming epilogue (V_r diag(f) as a GEMM operand): needed whenever two
+    // N x RP blocks of V do not fit in shared memory, which starts at N = 512 with a rank estimate above 24
     DevBuf bVf;
-    if (large_n) CK(bVf.alloc((size_t)N * kStreamMaxRank * 8, st));
+    CK(bVf.alloc((size_t)N * kStreamMaxRank * 8, st));
     CK(bG.alloc(((size_t)n * n + 8) * 8, st)); CK(bGn.alloc(((size_t)n * n + 8) * 8, st));
     CK(bG2.alloc(((size_t)n * n + 8) * 8, st));
     CK(bVs.alloc((size_t)n * n * 8, st)); CK(bVs2.alloc((size_t)n * n * 8, st));
