@@ -218,6 +218,24 @@ def test_rpca_3000_x_1000_with_returned_svd(largen):
     assert np.abs(s.Vt @ s.Vt.T - np.eye(1000)).max() < 1e-11
 
 
+def test_rank_above_32_with_n_above_512_takes_the_dense_device_path():
+    """512 < min(M,N) with a rank estimate of 40: outside the 32-column factored kernels.  tlsq_rpca_f64 repeats the solve
+    on the dense device path (full Jacobi SVT, exact stop test) instead of failing; device-pointer solves still report it."""
+    import torch
+    D = T.synth.lowrank_sparse_np(3000, 600, 40, 0.05, seed=7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        A, E, s, sv, info = T.rpca(D, iters=5, tol=0.0, return_info=True)
+        ref = O.rpca(D, iters=5, tol=0.0)
+    assert np.array_equal(info["hist"][:, 1], ref.hist[:, 1]) and ref.hist[-1, 1] == 40
+    assert relF(A, ref.A) < TOL and relF(E, ref.E) < TOL
+    assert np.allclose(info["hist"][:, 2], ref.hist[:, 2], rtol=1e-8)
+    assert np.allclose(s.S, ref.s.S, rtol=0, atol=1e-12 * ref.s.S[0])
+    with pytest.raises(T.TlsqError, match="rank estimate"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        T.rpca(torch.from_numpy(D).cuda(), iters=5, tol=0.0)
+
+
 def test_lowrankfilter_default_embedding_16k_samples_live_oracle():
     """n = 800 (default for 16 000 samples), even row count -> TMA SYRK at N = 800; oracle run on the host cores."""
     y, yn = T.synth.sinusoid_np(16_001, seed=9, noise=0.02)

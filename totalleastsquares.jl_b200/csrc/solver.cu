@@ -131,6 +131,9 @@ namespace {
 // cached between solves without touching the attributes of the device's default pool, which a co-resident allocator
 // (PyTorch) may be using
 thread_local cudaMemPool_t t_pool = nullptr;
+// set when a solve left the accelerated large-embedding path because its rank estimate outgrew the 32-column factors:
+// tlsq_rpca_f64 then repeats the solve on the dense device path (rpca_cb_host with the built-in hooks)
+thread_local bool t_rank_overflow = false;
 
 struct DevBuf {                  // stream-ordered device allocation, freed on scope exit
     void* p = nullptr;
@@ -142,7 +145,8 @@ struct DevBuf {                  // stream-ordered device allocation, freed on s
         return cudaMallocAsync(&p, bytes, s);
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; } }
+    ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -684,6 +688,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 ea.Zout = (want_z && Zbuf) ? Zbuf : nullptr;
                 ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
                 ea.vf_work = bVf.as<double>();
+                if (large_n && svp_guess > kStreamMaxRank) t_rank_overflow = true;
                 if (large_n && svp_guess > kStreamMaxRank)
                     return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: rank estimate %d > %d with min(M,N) = %lld > %d is outside "
                                    "the accelerated path", svp_guess, kStreamMaxRank, (long long)N, kEigSmallN);
@@ -1470,7 +1475,10 @@ int rpca_cb_host(tlsq_handle* h, const double* Dh, int64_t M, int64_t N, const R
     double* Z = bZ.as<double>(); double* W = bW.as<double>(); double* dscal = bScal.as<double>();
     EigScratch es;
     CKR(es.init(n, st));
-    std::vector<double> Zh(mn), Us((size_t)M * n), Ss(n), Vts((size_t)n * N), Usc((size_t)M * n), Vrc((size_t)n * N);
+    // host staging for the user callables only (none of it exists on the all-device fallback of tlsq_rpca_f64)
+    std::vector<double> Zh, Us, Ss, Vts, Usc, Vrc;
+    if (svd_fn || opn_fn) Zh.resize(mn);
+    if (svd_fn) { Us.resize((size_t)M * n); Ss.resize(n); Vts.resize((size_t)n * N); Usc.resize((size_t)M * n); Vrc.resize((size_t)n * N); }
     int64_t r_user = -1;                     // rank of the last user SVD (-1: the last SVD was the built-in one)
     CK(cudaMemcpyAsync(D, Dh, mn * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(A, 0, mn * 8, st));
@@ -1777,7 +1785,18 @@ int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double 
     o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
     bool host_copied = false;                  // A / E went to the host while the SVD was still being computed
     o.hA = A; o.hE = E; o.host_copied = &host_copied;
-    CKR(rpca_dev(h, bD.as<double>(), M, N, p, o));
+    t_rank_overflow = false;
+    const int rc = rpca_dev(h, bD.as<double>(), M, N, p, o);
+    if (rc == TLSQ_ERR_UNSUPPORTED && t_rank_overflow && h->nranks == 1) {
+        // 512 < min(M,N) <= 2048 with a rank estimate above 32: outside the factored kernels.  Repeat the solve on the
+        // dense device path (full Jacobi SVT + exact stop test every iteration: the reference's loop statement by
+        // statement, slower but without a rank limit) instead of failing.
+        t_rank_overflow = false;
+        CK(cudaStreamSynchronize(st));
+        bD.release(); bA.release(); bE.release(); bU.release(); bS.release(); bVt.release();
+        return rpca_cb_host(h, D, M, N, p, nullptr, nullptr, nullptr, A, E, U, S, Vt, sv, iters_done, converged, hist);
+    }
+    if (rc != TLSQ_OK) return rc;
     if (A && !host_copied) CK(cudaMemcpyAsync(A, o.A, mn * 8, cudaMemcpyDeviceToHost, st));
     if (E && !host_copied) CK(cudaMemcpyAsync(E, o.E, mn * 8, cudaMemcpyDeviceToHost, st));
     if (U) CK(cudaMemcpyAsync(U, o.U, (size_t)M * d * 8, cudaMemcpyDeviceToHost, st));
