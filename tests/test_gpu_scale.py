@@ -236,6 +236,22 @@ def test_rank_above_32_with_n_above_512_takes_the_dense_device_path():
         T.rpca(torch.from_numpy(D).cuda(), iters=5, tol=0.0)
 
 
+def test_hankel_true_with_n_above_512_takes_the_dense_device_path():
+    """hankel=true (soft_hankel! every iteration, src/robustPCA.jl:214-216, 234-236) on a 1801 x 600 Hankel matrix: the
+    accelerated hankel=true kernels stop at min(M,N) = 512; host-buffer solves continue on the dense device path."""
+    rng = np.random.default_rng(11)
+    t = np.arange(2400)
+    y = np.sin(0.01 * t) + 0.5 * np.sin(0.037 * t) + 0.05 * rng.standard_normal(2400)
+    y[rng.random(2400) < 0.02] += 3.0
+    H = O.hankel(y, 600)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        A, E, s, sv, info = T.rpca(H, hankel=True, iters=4, tol=0.0, return_info=True)
+        ref = O.rpca(H, hankel=True, iters=4, tol=0.0)
+    assert np.array_equal(info["hist"][:, 1], ref.hist[:, 1])
+    assert relF(A, ref.A) < TOL and relF(E, ref.E) < TOL
+
+
 def test_lowrankfilter_default_embedding_16k_samples_live_oracle():
     """n = 800 (default for 16 000 samples), even row count -> TMA SYRK at N = 800; oracle run on the host cores."""
     y, yn = T.synth.sinusoid_np(16_001, seed=9, noise=0.02)

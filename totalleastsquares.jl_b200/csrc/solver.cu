@@ -131,9 +131,10 @@ namespace {
 // cached between solves without touching the attributes of the device's default pool, which a co-resident allocator
 // (PyTorch) may be using
 thread_local cudaMemPool_t t_pool = nullptr;
-// set when a solve left the accelerated large-embedding path because its rank estimate outgrew the 32-column factors:
+// set when a solve left the accelerated large-embedding path (rank estimate beyond the 32-column factors, or hankel=true
+// with min(M,N) > 512):
 // tlsq_rpca_f64 then repeats the solve on the dense device path (rpca_cb_host with the built-in hooks)
-thread_local bool t_rank_overflow = false;
+thread_local bool t_dense_fallback = false;
 
 struct DevBuf {                  // stream-ordered device allocation, freed on scope exit
     void* p = nullptr;
@@ -312,6 +313,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
     // large embeddings (n > 512): always the two-kernel pipeline on a materialised W (column-chunked streaming epilogue,
     // T = W V_r by GEMM); the Gram takes the TMA SYRK when the shape allows it, else the generic DMMA kernel on W
     const bool large_n = N > kEigSmallN;
+    if (large_n && hk) t_dense_fallback = true;           // host-buffer solves repeat on the dense device path
     if (large_n && hk)
         return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: hankel=true is limited to min(M,N) <= %d", kEigSmallN);
     const bool can_legacy = (syrk_ok || large_n) && !hk;
@@ -688,7 +690,7 @@ int rpca_core_once(tlsq_handle* h, MatSrc D, bool hankel, int64_t M, int64_t N, 
                 ea.Zout = (want_z && Zbuf) ? Zbuf : nullptr;
                 ea.Wn = Wbuf; ea.im_next = 1.0 / mu_next; ea.eps_next = p.lambda / mu_next;
                 ea.vf_work = bVf.as<double>();
-                if (large_n && svp_guess > kStreamMaxRank) t_rank_overflow = true;
+                if (large_n && svp_guess > kStreamMaxRank) t_dense_fallback = true;
                 if (large_n && svp_guess > kStreamMaxRank)
                     return set_err(TLSQ_ERR_UNSUPPORTED, "rpca: rank estimate %d > %d with min(M,N) = %lld > %d is outside "
                                    "the accelerated path", svp_guess, kStreamMaxRank, (long long)N, kEigSmallN);
@@ -1785,13 +1787,13 @@ int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double 
     o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
     bool host_copied = false;                  // A / E went to the host while the SVD was still being computed
     o.hA = A; o.hE = E; o.host_copied = &host_copied;
-    t_rank_overflow = false;
+    t_dense_fallback = false;
     const int rc = rpca_dev(h, bD.as<double>(), M, N, p, o);
-    if (rc == TLSQ_ERR_UNSUPPORTED && t_rank_overflow && h->nranks == 1) {
-        // 512 < min(M,N) <= 2048 with a rank estimate above 32: outside the factored kernels.  Repeat the solve on the
+    if (rc == TLSQ_ERR_UNSUPPORTED && t_dense_fallback && h->nranks == 1) {
+        // 512 < min(M,N) <= 2048 with a rank estimate above 32, or with hankel=true: outside the factored kernels.  Repeat the solve on the
         // dense device path (full Jacobi SVT + exact stop test every iteration: the reference's loop statement by
         // statement, slower but without a rank limit) instead of failing.
-        t_rank_overflow = false;
+        t_dense_fallback = false;
         CK(cudaStreamSynchronize(st));
         bD.release(); bA.release(); bE.release(); bU.release(); bS.release(); bVt.release();
         return rpca_cb_host(h, D, M, N, p, nullptr, nullptr, nullptr, A, E, U, S, Vt, sv, iters_done, converged, hist);
