@@ -1482,7 +1482,7 @@ int rpca_cb_host(tlsq_handle* h, const double* Dh, int64_t M, int64_t N, const R
     if (svd_fn || opn_fn) Zh.resize(mn);
     if (svd_fn) { Us.resize((size_t)M * n); Ss.resize(n); Vts.resize((size_t)n * N); Usc.resize((size_t)M * n); Vrc.resize((size_t)n * N); }
     int64_t r_user = -1;                     // rank of the last user SVD (-1: the last SVD was the built-in one)
-    CK(cudaMemcpyAsync(D, Dh, mn * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D, Dh, mn * 8, cudaMemcpyDefault, st));      // host or device pointer (UVA)
     CK(cudaMemsetAsync(A, 0, mn * 8, st));
     CK(cudaMemsetAsync(dscal, 0, 64, st));
     // ---- setup (:174-185) ----
@@ -1578,8 +1578,8 @@ int rpca_cb_host(tlsq_handle* h, const double* Dh, int64_t M, int64_t N, const R
         CK(launch_unhankel(E, M, N, 1, M + N - 1, bMean.as<double>(), st, L));
         CK(launch_soft_hankel_apply(E, M, N, bMean.as<double>(), p.lambda / mu, sms, st, L));
     }
-    if (Ah) CK(cudaMemcpyAsync(Ah, A, mn * 8, cudaMemcpyDeviceToHost, st));
-    if (Eh) CK(cudaMemcpyAsync(Eh, E, mn * 8, cudaMemcpyDeviceToHost, st));
+    if (Ah) CK(cudaMemcpyAsync(Ah, A, mn * 8, cudaMemcpyDefault, st));
+    if (Eh) CK(cudaMemcpyAsync(Eh, E, mn * 8, cudaMemcpyDefault, st));
     CK(cudaStreamSynchronize(st));
     // s: the SVD object of the LAST SVT input (:238) -- the user's, or the built-in one to LAPACK accuracy
     if (Uh || Sh || Vth) {
@@ -1598,16 +1598,16 @@ int rpca_cb_host(tlsq_handle* h, const double* Dh, int64_t M, int64_t N, const R
             const double* T = W;
             if (!tall) { CK(launch_transpose(W, M, N, bXt.as<double>(), st, L)); T = bXt.as<double>(); }
             CKR(svd_tall_dev(h, T, m, n, es, bU.as<double>(), bS.as<double>(), bVt.as<double>()));
-            if (Sh) CK(cudaMemcpyAsync(Sh, bS.as<double>(), (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            if (Sh) CK(cudaMemcpyAsync(Sh, bS.as<double>(), (size_t)n * 8, cudaMemcpyDefault, st));
             if (tall) {
-                if (Uh) CK(cudaMemcpyAsync(Uh, bU.as<double>(), (size_t)M * n * 8, cudaMemcpyDeviceToHost, st));
-                if (Vth) CK(cudaMemcpyAsync(Vth, bVt.as<double>(), (size_t)n * N * 8, cudaMemcpyDeviceToHost, st));
+                if (Uh) CK(cudaMemcpyAsync(Uh, bU.as<double>(), (size_t)M * n * 8, cudaMemcpyDefault, st));
+                if (Vth) CK(cudaMemcpyAsync(Vth, bVt.as<double>(), (size_t)n * N * 8, cudaMemcpyDefault, st));
             } else {
                 // W' = U_t S V_t'  =>  W = V_t S U_t':  U = V_t (M x d) = (Vt_t)',  Vt = U_t' (d x N)
                 if (Uh) { CK(launch_transpose(bVt.as<double>(), n, n, bB1.as<double>(), st, L));
-                          CK(cudaMemcpyAsync(Uh, bB1.as<double>(), (size_t)M * n * 8, cudaMemcpyDeviceToHost, st)); }
+                          CK(cudaMemcpyAsync(Uh, bB1.as<double>(), (size_t)M * n * 8, cudaMemcpyDefault, st)); }
                 if (Vth) { CK(launch_transpose(bU.as<double>(), N, n, bT.as<double>(), st, L));
-                           CK(cudaMemcpyAsync(Vth, bT.as<double>(), (size_t)n * N * 8, cudaMemcpyDeviceToHost, st)); }
+                           CK(cudaMemcpyAsync(Vth, bT.as<double>(), (size_t)n * N * 8, cudaMemcpyDefault, st)); }
             }
             CK(cudaStreamSynchronize(st));
         }
@@ -1759,7 +1759,15 @@ int tlsq_rpca_f64_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, dou
     RpcaOut o;
     o.A = A; o.E = E; o.U = U; o.S = S; o.Vt = Vt; o.sv = sv; o.iters_done = iters_done; o.converged = converged;
     o.hist = hist;
-    return rpca_dev(h, D, M, N, p, o);
+    t_dense_fallback = false;
+    const int rc = rpca_dev(h, D, M, N, p, o);
+    if (rc == TLSQ_ERR_UNSUPPORTED && t_dense_fallback && h->nranks == 1) {
+        // see tlsq_rpca_f64: continue on the dense device path (its copies are location-agnostic)
+        t_dense_fallback = false;
+        CK(cudaStreamSynchronize(h->stream));
+        return rpca_cb_host(h, D, M, N, p, nullptr, nullptr, nullptr, A, E, U, S, Vt, sv, iters_done, converged, hist);
+    }
+    return rc;
 }
 
 int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double lambda, int64_t maxrank,
