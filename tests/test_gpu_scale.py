@@ -254,6 +254,28 @@ def test_hankel_true_with_n_above_512_takes_the_dense_device_path():
     assert relF(A, ref.A) < TOL and relF(E, ref.E) < TOL
 
 
+def test_lowrankfilter_default_embedding_with_rank_above_32():
+    """lowrankfilter(y) with the default n = 600 on twenty sinusoids + outliers: the rank estimate runs 32, 36, ... 82, past
+    the 32-column factors of the implicit-Hankel kernels; the solve continues on the dense device path (materialised
+    embedding) and still matches the reference's iteration count, rank history and filtered signal."""
+    rng = np.random.default_rng(5)
+    Ns = 12000
+    t = np.arange(Ns)
+    freqs = 0.02 + 0.9 * rng.random(20)
+    y0 = sum(np.sin(f * t + rng.random() * 6.28) * (0.5 + rng.random()) for f in freqs)
+    y = y0 + 0.05 * rng.standard_normal(Ns)
+    y[rng.random(Ns) < 0.01] += 5.0
+    yf, info = T.lowrankfilter(y, return_info=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = O.rpca(O.hankel(y, 600), tol=1e-3)
+    assert ref.hist[:, 1].max() > 32
+    assert info["iters"] == ref.iters and info["sv"] == ref.sv
+    assert np.array_equal(info["hist"][:, 1], ref.hist[:, 1])
+    assert relF(yf, O.unhankel_fast(ref.A)) < TOL
+    assert np.mean((yf - y0) ** 2) / np.mean(y0 ** 2) < 1e-3
+
+
 def test_lowrankfilter_default_embedding_16k_samples_live_oracle():
     """n = 800 (default for 16 000 samples), even row count -> TMA SYRK at N = 800; oracle run on the host cores."""
     y, yn = T.synth.sinusoid_np(16_001, seed=9, noise=0.02)

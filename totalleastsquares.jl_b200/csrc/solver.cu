@@ -1058,6 +1058,25 @@ int rpca_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, const RpcaPa
     return TLSQ_OK;
 }
 
+int rpca_cb_host(tlsq_handle* h, const double* Dh, int64_t M, int64_t N, const RpcaParams& p, tlsq_svd_fn svd_fn,
+                 tlsq_opnorm_fn opn_fn, void* user, double* Ah, double* Eh, double* Uh, double* Sh, double* Vth,
+                 int64_t* sv_out, int64_t* iters_done, int32_t* converged, double* hist);
+
+// rpca_dev, continued on the dense device path (rpca_cb_host with its built-in hooks: full Jacobi SVT + exact stop test
+// every iteration, no rank limit) when a single-GPU solve leaves the accelerated kernels -- 512 < min(M,N) <= 2048 with
+// a rank estimate above 32, or with hankel=true.  Slower, but the reference has no such limit either.
+int rpca_dev_any(tlsq_handle* h, const double* D, int64_t M, int64_t N, const RpcaParams& p, const RpcaOut& o) {
+    t_dense_fallback = false;
+    const int rc = rpca_dev(h, D, M, N, p, o);
+    if (rc == TLSQ_ERR_UNSUPPORTED && t_dense_fallback && h->nranks == 1) {
+        t_dense_fallback = false;
+        CK(cudaStreamSynchronize(h->stream));
+        return rpca_cb_host(h, D, M, N, p, nullptr, nullptr, nullptr, o.A, o.E, o.U, o.S, o.Vt, o.sv, o.iters_done,
+                            o.converged, o.hist);
+    }
+    return rc;
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // Grassmann averages core (device pointers)
 // ----------------------------------------------------------------------------------------------------------
@@ -1270,11 +1289,23 @@ int lowrankfilter_dev(tlsq_handle* h, const double* y, int64_t Ns, int64_t n, in
                            kEigMaxN);
         CKR(check_rpca_args(K, n, p));
         MatSrc src{y, lag};                    // implicit Hankel: H[k,l] = y[k*lag + l], never materialised
-        CKR(rpca_core(h, src, true, K, n, p, o));
+        t_dense_fallback = false;
+        const int rc = rpca_core(h, src, true, K, n, p, o);
+        if (rc == TLSQ_ERR_UNSUPPORTED && t_dense_fallback && h->nranks == 1) {
+            // n > 512 and a rank estimate above 32: materialise the embedding, continue on the dense device path
+            t_dense_fallback = false;
+            CK(cudaStreamSynchronize(st));
+            CK(bH.alloc((size_t)K * n * 8, st));
+            CK(launch_hankel(y, K, n, lag, bH.as<double>(), st, &h->launches));
+            CKR(rpca_cb_host(h, bH.as<double>(), K, n, p, nullptr, nullptr, nullptr, o.A, nullptr, nullptr, nullptr, nullptr,
+                             sv, iters_done, converged, hist));
+        } else if (rc != TLSQ_OK) {
+            return rc;
+        }
     } else {
         CK(bH.alloc((size_t)K * n * 8, st));
         CK(launch_hankel(y, K, n, lag, bH.as<double>(), st, &h->launches));
-        CKR(rpca_dev(h, bH.as<double>(), K, n, p, o));
+        CKR(rpca_dev_any(h, bH.as<double>(), K, n, p, o));
     }
     CK(launch_unhankel(o.A, K, n, lag, Ns, yf, st, &h->launches));                       // :127
     CK(cudaStreamSynchronize(st));
@@ -1367,7 +1398,7 @@ int lowrankfilter_general_dev(tlsq_handle* h, const double* y, int64_t Ns, int64
         if (!(p.lambda > 0.0)) p.lambda = 1.0 / sqrt((double)(K > Lc ? K : Lc));           // :157
         RpcaOut o;
         o.A = A; o.sv = sv; o.iters_done = iters_done; o.converged = converged; o.hist = hist;
-        CKR(rpca_dev(h, H, K, Lc, p, o));                                                 // :122
+        CKR(rpca_dev_any(h, H, K, Lc, p, o));                                             // :122
     }
     if (Dch == 1) CK(launch_unhankel(A, K, n, lag, Ns, yf, st, L));                       // :127
     else CK(launch_unhankel_mc(A, K, n, lag, Ns, Dch, yf, st, L));
@@ -1759,15 +1790,7 @@ int tlsq_rpca_f64_dev(tlsq_handle* h, const double* D, int64_t M, int64_t N, dou
     RpcaOut o;
     o.A = A; o.E = E; o.U = U; o.S = S; o.Vt = Vt; o.sv = sv; o.iters_done = iters_done; o.converged = converged;
     o.hist = hist;
-    t_dense_fallback = false;
-    const int rc = rpca_dev(h, D, M, N, p, o);
-    if (rc == TLSQ_ERR_UNSUPPORTED && t_dense_fallback && h->nranks == 1) {
-        // see tlsq_rpca_f64: continue on the dense device path (its copies are location-agnostic)
-        t_dense_fallback = false;
-        CK(cudaStreamSynchronize(h->stream));
-        return rpca_cb_host(h, D, M, N, p, nullptr, nullptr, nullptr, A, E, U, S, Vt, sv, iters_done, converged, hist);
-    }
-    return rc;
+    return rpca_dev_any(h, D, M, N, p, o);
 }
 
 int tlsq_rpca_f64(tlsq_handle* h, const double* D, int64_t M, int64_t N, double lambda, int64_t maxrank,
